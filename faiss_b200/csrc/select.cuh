@@ -1,0 +1,202 @@
+// faiss_b200 -- k-selection primitive (device side).
+//
+// Role of the reference's BlockSelect / WarpSelect + merge networks
+// (faiss/gpu/utils/Select.cuh:147-343,439-594; MergeNetworkWarp.cuh; MergeNetworkBlock.cuh),
+// re-designed: one shared-memory "sorted list + candidate buffer" per selection problem, owned by
+// a single warp.  Candidates that beat the current k-th key are appended to the buffer with a
+// ballot-compacted write; when the buffer is more than half full the warp sorts it (bitonic) and
+// folds it into the list with one bitonic half-merge (the list stays sorted, only the best LIST
+// entries survive).  Steady-state cost per element is one compare + one vote.
+//
+// Ordering: smaller key is better; ties are broken by smaller id, i.e. the total order
+// (key asc, id asc) that the reference CPU result handlers produce
+// (faiss/utils/ordered_key_value.h:40-75, faiss/impl/ResultHandler.h:275-282).  Inner-product
+// search negates keys on the way in and on the way out.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+
+namespace fb200 {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename IdT>
+struct IdLimits;
+template <>
+struct IdLimits<int> {
+    static __host__ __device__ constexpr int max() {
+        return 0x7fffffff;
+    }
+};
+template <>
+struct IdLimits<long long> {
+    static __host__ __device__ constexpr long long max() {
+        return 0x7fffffffffffffffLL;
+    }
+};
+
+template <typename IdT>
+__device__ __forceinline__ bool kv_less(float ka, IdT ia, float kb, IdT ib) {
+    return (ka < kb) || (ka == kb && ia < ib);
+}
+
+__device__ __forceinline__ int lane_id() {
+    return threadIdx.x & 31;
+}
+
+// Shared-memory top-k list owned by one warp.
+//   keys/ids : arrays of LIST + BUF entries; [0, LIST) sorted ascending, [LIST, LIST+BUF) buffer
+//   LIST     : power of two, >= BUF, >= k
+//   BUF      : power of two (64 / 128 / 256); flush when more than BUF/2 are pending, so a caller
+//              may append up to BUF/2 entries between two `maybe_flush` calls.
+template <typename IdT>
+struct SmemTopK {
+    float* keys;
+    IdT* ids;
+    int LIST;
+    int BUF;
+    int k;
+
+    __device__ __forceinline__ static size_t bytes(int LIST, int BUF) {
+        return size_t(LIST + BUF) * (sizeof(float) + sizeof(IdT));
+    }
+
+    // warp-collective
+    __device__ void init() {
+        for (int i = lane_id(); i < LIST + BUF; i += 32) {
+            keys[i] = CUDART_INF_F;
+            ids[i] = IdLimits<IdT>::max();
+        }
+        __syncwarp();
+    }
+
+    __device__ __forceinline__ float threshold() const {
+        return keys[k - 1];
+    }
+
+    // warp-collective: sort buffer (n_pending valid entries), merge into list.
+    __device__ void flush(int n_pending) {
+        const int lane = lane_id();
+        float* bk = keys + LIST;
+        IdT* bi = ids + LIST;
+        // size of the sub-buffer to sort: next pow2 >= n_pending (>= 32)
+        int n = 32;
+        while (n < n_pending)
+            n <<= 1;
+        for (int i = n_pending + lane; i < n; i += 32) {
+            bk[i] = CUDART_INF_F;
+            bi[i] = IdLimits<IdT>::max();
+        }
+        __syncwarp();
+        // bitonic sort ascending of bk[0..n)
+        for (int size = 2; size <= n; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = lane; t < (n >> 1); t += 32) {
+                    int a = 2 * stride * (t / stride) + (t % stride);
+                    int b = a + stride;
+                    bool asc = ((a & size) == 0);
+                    float ka = bk[a], kb = bk[b];
+                    IdT ia = bi[a], ib = bi[b];
+                    bool sw = asc ? kv_less(kb, ib, ka, ia) : kv_less(ka, ia, kb, ib);
+                    if (sw) {
+                        bk[a] = kb;
+                        bk[b] = ka;
+                        bi[a] = ib;
+                        bi[b] = ia;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // half-merge stage 0: L[LIST-1-j] = min(L[LIST-1-j], B[j])  (B ascending, L ascending)
+        for (int j = lane; j < n; j += 32) {
+            int a = LIST - 1 - j;
+            float ka = keys[a], kb = bk[j];
+            IdT ia = ids[a], ib = bi[j];
+            if (kv_less(kb, ib, ka, ia)) {
+                keys[a] = kb;
+                ids[a] = ib;
+            }
+        }
+        __syncwarp();
+        // L is now bitonic and holds the LIST best; finish with a bitonic merge
+        for (int stride = LIST >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (LIST >> 1); t += 32) {
+                int a = 2 * stride * (t / stride) + (t % stride);
+                int b = a + stride;
+                float ka = keys[a], kb = keys[b];
+                IdT ia = ids[a], ib = ids[b];
+                if (kv_less(kb, ib, ka, ia)) {
+                    keys[a] = kb;
+                    keys[b] = ka;
+                    ids[a] = ib;
+                    ids[b] = ia;
+                }
+            }
+            __syncwarp();
+        }
+    }
+};
+
+// Warp-private streaming interface over SmemTopK: every lane offers one (key,id) per call.
+template <typename IdT>
+struct WarpTopK {
+    SmemTopK<IdT> q;
+    int cnt;   // pending entries in the buffer (warp-uniform)
+    float thr; // key of the current k-th (warp-uniform)
+
+    __device__ void init(float* keys, IdT* ids, int LIST, int BUF, int k) {
+        q.keys = keys;
+        q.ids = ids;
+        q.LIST = LIST;
+        q.BUF = BUF;
+        q.k = k;
+        q.init();
+        cnt = 0;
+        thr = CUDART_INF_F;
+    }
+
+    // warp-collective; `valid` false lanes offer nothing.  NaN keys never pass.
+    __device__ __forceinline__ void add(bool valid, float key, IdT id) {
+        bool pass = valid && (key <= thr);
+        unsigned m = __ballot_sync(kFullMask, pass);
+        if (m) {
+            int pos = cnt + __popc(m & ((1u << lane_id()) - 1u));
+            if (pass) {
+                q.keys[q.LIST + pos] = key;
+                q.ids[q.LIST + pos] = id;
+            }
+            cnt += __popc(m);
+            if (cnt > q.BUF - 32) {
+                __syncwarp();
+                q.flush(cnt);
+                cnt = 0;
+                thr = q.threshold();
+            }
+        }
+    }
+
+    __device__ void finish() {
+        __syncwarp();
+        if (cnt > 0) {
+            q.flush(cnt);
+            cnt = 0;
+        }
+        thr = q.threshold();
+        __syncwarp();
+    }
+};
+
+// order-preserving float -> uint32 (for packed 64-bit atomicMin argmin)
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+} // namespace fb200
