@@ -1,0 +1,664 @@
+// faiss_b200 -- the C ABI (include/faiss_b200_c.h).  Exceptions -> status codes + thread-local
+// message, exactly as the reference does (c_api/macros_impl.h:22-36, c_api/error_impl.cpp:15).
+#include <cstring>
+#include <sstream>
+
+#include "faiss_b200_c.h"
+#include "index.h"
+
+using namespace fb200;
+
+static thread_local std::string g_last_error;
+
+#define CATCH_AND_HANDLE                              \
+    catch (const fb200::FaissException& e) {          \
+        g_last_error = e.what();                      \
+        return -2;                                    \
+    }                                                 \
+    catch (const std::exception& e) {                 \
+        g_last_error = e.what();                      \
+        return -4;                                    \
+    }                                                 \
+    catch (...) {                                     \
+        g_last_error = "unknown exception";           \
+        return -1;                                    \
+    }                                                 \
+    return 0;
+
+struct FaissStandardGpuResources_H {
+    std::shared_ptr<StandardGpuResources> res;
+};
+struct FaissIndex_H {
+    Index* index;
+    // keeps the resources alive as long as an index uses them
+    std::shared_ptr<StandardGpuResources> res;
+};
+
+static Index* IX(const FaissIndex* p) {
+    if (!p || !p->index)
+        FB_THROW_MSG("null index handle");
+    return p->index;
+}
+template <typename T>
+static T* AS(const FaissIndex* p, const char* what) {
+    T* t = dynamic_cast<T*>(IX(p));
+    if (!t)
+        FB_THROW_FMT("index handle is not a %s", what);
+    return t;
+}
+static std::shared_ptr<StandardGpuResources> RES(FaissStandardGpuResources* r) {
+    if (!r || !r->res)
+        FB_THROW_MSG("null resources handle");
+    return r->res;
+}
+static MetricType MT(FaissMetricType m) {
+    if (m != ::METRIC_L2 && m != ::METRIC_INNER_PRODUCT)
+        FB_THROW_MSG("unsupported metric type");
+    return m == ::METRIC_L2 ? fb200::METRIC_L2 : fb200::METRIC_INNER_PRODUCT;
+}
+
+extern "C" {
+
+const char* faiss_get_last_error(void) {
+    return g_last_error.c_str();
+}
+const char* faiss_b200_version(void) {
+    return "faiss_b200 0.1 (sm_100a)";
+}
+
+// ---------------------------------------------------------------- resources
+int faiss_StandardGpuResources_new(FaissStandardGpuResources** p) {
+    try {
+        auto* h = new FaissStandardGpuResources_H();
+        h->res = std::make_shared<StandardGpuResources>();
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+void faiss_StandardGpuResources_free(FaissStandardGpuResources* r) {
+    delete r;
+}
+int faiss_StandardGpuResources_noTempMemory(FaissStandardGpuResources* r) {
+    try {
+        RES(r)->noTempMemory();
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_setTempMemory(FaissStandardGpuResources* r, size_t size) {
+    try {
+        RES(r)->setTempMemory(size);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_setPinnedMemory(FaissStandardGpuResources* r, size_t size) {
+    try {
+        RES(r)->setPinnedMemory(size);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_setDefaultStream(FaissStandardGpuResources* r, int device, void* stream) {
+    try {
+        RES(r)->setDefaultStream(device, (cudaStream_t)stream);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_setDefaultNullStreamAllDevices(FaissStandardGpuResources* r) {
+    try {
+        RES(r)->setDefaultNullStreamAllDevices();
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_getDefaultStream(FaissStandardGpuResources* r, int device, void** out) {
+    try {
+        *out = (void*)RES(r)->getDefaultStream(device);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_syncDefaultStream(FaissStandardGpuResources* r, int device) {
+    try {
+        DeviceScope s(device);
+        RES(r)->syncDefaultStream(device);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_getMemoryInfo(FaissStandardGpuResources* r, char* buf, size_t buflen) {
+    try {
+        auto info = RES(r)->getMemoryInfo();
+        std::ostringstream os;
+        os << "{";
+        bool firstD = true;
+        for (auto& dv : info) {
+            if (!firstD)
+                os << ",";
+            firstD = false;
+            os << "\"" << dv.first << "\":{";
+            bool first = true;
+            for (auto& kv : dv.second) {
+                if (!first)
+                    os << ",";
+                first = false;
+                os << "\"" << kv.first << "\":[" << kv.second.first << "," << kv.second.second << "]";
+            }
+            os << "}";
+        }
+        os << "}";
+        std::string s = os.str();
+        FB_THROW_IF_NOT_MSG(s.size() + 1 <= buflen, "buffer too small");
+        memcpy(buf, s.c_str(), s.size() + 1);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_getTempMemoryAvailable(FaissStandardGpuResources* r, int device, size_t* out) {
+    try {
+        RES(r)->initializeForDevice(device);
+        *out = RES(r)->getTempMemoryAvailable(device);
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- generic index
+void faiss_Index_free(FaissIndex* p) {
+    if (p) {
+        delete p->index;
+        delete p;
+    }
+}
+int faiss_Index_d(const FaissIndex* p) {
+    return p && p->index ? p->index->d : 0;
+}
+int faiss_Index_is_trained(const FaissIndex* p) {
+    return p && p->index ? (int)p->index->is_trained : 0;
+}
+idx_t faiss_Index_ntotal(const FaissIndex* p) {
+    return p && p->index ? p->index->ntotal : 0;
+}
+FaissMetricType faiss_Index_metric_type(const FaissIndex* p) {
+    return p && p->index && p->index->metric_type == fb200::METRIC_INNER_PRODUCT ? ::METRIC_INNER_PRODUCT : ::METRIC_L2;
+}
+int faiss_Index_verbose(const FaissIndex* p) {
+    return p && p->index ? (int)p->index->verbose : 0;
+}
+void faiss_Index_set_verbose(FaissIndex* p, int v) {
+    if (p && p->index)
+        p->index->verbose = v != 0;
+}
+int faiss_Index_train(FaissIndex* p, idx_t n, const float* x) {
+    try {
+        IX(p)->train(n, x);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_add(FaissIndex* p, idx_t n, const float* x) {
+    try {
+        IX(p)->add(n, x);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_add_with_ids(FaissIndex* p, idx_t n, const float* x, const idx_t* xids) {
+    try {
+        IX(p)->add_with_ids(n, x, xids);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_search(const FaissIndex* p, idx_t n, const float* x, idx_t k, float* D, idx_t* I) {
+    try {
+        IX(p)->search(n, x, k, D, I);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_assign(FaissIndex* p, idx_t n, const float* x, idx_t* labels, idx_t k) {
+    try {
+        IX(p)->assign(n, x, labels, k);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_reset(FaissIndex* p) {
+    try {
+        IX(p)->reset();
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_reconstruct(const FaissIndex* p, idx_t key, float* out) {
+    try {
+        IX(p)->reconstruct(key, out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_reconstruct_n(const FaissIndex* p, idx_t i0, idx_t ni, float* out) {
+    try {
+        IX(p)->reconstruct_n(i0, ni, out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_reconstruct_batch(const FaissIndex* p, idx_t n, const idx_t* keys, float* out) {
+    try {
+        IX(p)->reconstruct_batch(n, keys, out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_compute_residual(const FaissIndex* p, const float* x, float* r, idx_t key) {
+    try {
+        IX(p)->compute_residual(x, r, key);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_Index_compute_residual_n(const FaissIndex* p, idx_t n, const float* x, float* r, const idx_t* keys) {
+    try {
+        IX(p)->compute_residual_n(n, x, r, keys);
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- GpuIndexFlat
+int faiss_GpuIndexFlat_new(
+        FaissGpuIndex** p,
+        FaissStandardGpuResources* r,
+        int d,
+        FaissMetricType metric,
+        int device,
+        int use_tc) {
+    try {
+        GpuIndexFlatConfig c;
+        c.device = device;
+        c.useTensorCores = use_tc != 0;
+        auto res = RES(r);
+        auto* h = new FaissIndex_H();
+        h->res = res;
+        h->index = new GpuIndexFlat(res, d, MT(metric), c);
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexFlatL2_new(FaissGpuIndex** p, FaissStandardGpuResources* r, int d, int device) {
+    return faiss_GpuIndexFlat_new(p, r, d, ::METRIC_L2, device, 1);
+}
+int faiss_GpuIndexFlatIP_new(FaissGpuIndex** p, FaissStandardGpuResources* r, int d, int device) {
+    return faiss_GpuIndexFlat_new(p, r, d, ::METRIC_INNER_PRODUCT, device, 1);
+}
+int faiss_GpuIndexFlat_copyFrom(FaissGpuIndex* p, idx_t n, const float* xb) {
+    try {
+        AS<GpuIndexFlat>(p, "GpuIndexFlat")->copyFrom(n, xb);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexFlat_copyTo(const FaissGpuIndex* p, float* out) {
+    try {
+        AS<GpuIndexFlat>(p, "GpuIndexFlat")->copyTo(out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexFlat_setUseTensorCores(FaissGpuIndex* p, int enable) {
+    try {
+        AS<GpuIndexFlat>(p, "GpuIndexFlat")->setUseTensorCores(enable != 0);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexFlat_lastSearchInfo(const FaissGpuIndex* p, int* out2) {
+    try {
+        auto* f = AS<GpuIndexFlat>(p, "GpuIndexFlat");
+        out2[0] = f->lastSearchUsedTensorCores;
+        out2[1] = f->lastSearchFallbackQueries;
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- GpuIndexIVF
+int faiss_GpuIndexIVF_set_nprobe(FaissGpuIndex* p, size_t nprobe) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->nprobe = nprobe;
+    }
+    CATCH_AND_HANDLE
+}
+size_t faiss_GpuIndexIVF_nprobe(const FaissGpuIndex* p) {
+    auto* i = p ? dynamic_cast<GpuIndexIVF*>(p->index) : nullptr;
+    return i ? i->nprobe : 0;
+}
+size_t faiss_GpuIndexIVF_nlist(const FaissGpuIndex* p) {
+    auto* i = p ? dynamic_cast<GpuIndexIVF*>(p->index) : nullptr;
+    return i ? (size_t)i->nlist : 0;
+}
+int faiss_GpuIndexIVF_set_clustering(FaissGpuIndex* p, int niter, int seed, int maxppc) {
+    try {
+        auto* i = AS<GpuIndexIVF>(p, "GpuIndexIVF");
+        if (niter > 0)
+            i->cp.niter = niter;
+        if (seed >= 0)
+            i->cp.seed = seed;
+        if (maxppc > 0)
+            i->cp.max_points_per_centroid = maxppc;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_reserveMemory(FaissGpuIndex* p, size_t n) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->reserveMemory(n);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_reclaimMemory(FaissGpuIndex* p, size_t* out) {
+    try {
+        size_t r = AS<GpuIndexIVF>(p, "GpuIndexIVF")->reclaimMemory();
+        if (out)
+            *out = r;
+    }
+    CATCH_AND_HANDLE
+}
+size_t faiss_GpuIndexIVF_get_list_size(const FaissGpuIndex* p, size_t l) {
+    auto* i = p ? dynamic_cast<GpuIndexIVF*>(p->index) : nullptr;
+    if (!i || (idx_t)l >= i->nlist)
+        return 0;
+    return (size_t)i->getListLength((idx_t)l);
+}
+int faiss_GpuIndexIVF_getListVectorData(const FaissGpuIndex* p, size_t l, uint8_t* out) {
+    try {
+        auto v = AS<GpuIndexIVF>(p, "GpuIndexIVF")->getListVectorData((idx_t)l);
+        if (!v.empty())
+            memcpy(out, v.data(), v.size());
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_getListIndices(const FaissGpuIndex* p, size_t l, idx_t* out) {
+    try {
+        auto v = AS<GpuIndexIVF>(p, "GpuIndexIVF")->getListIndices((idx_t)l);
+        if (!v.empty())
+            memcpy(out, v.data(), v.size() * sizeof(idx_t));
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_setCoarseCentroids(FaissGpuIndex* p, const float* c) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->setCoarseCentroids(c);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_getCoarseCentroids(const FaissGpuIndex* p, float* out) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->getCoarseCentroids(out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_setList(FaissGpuIndex* p, size_t l, idx_t len, const uint8_t* codes, const idx_t* ids) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->setList((idx_t)l, len, codes, ids);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_set_is_trained(FaissGpuIndex* p, int v) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->is_trained = v != 0;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVF_search_preassigned(
+        const FaissGpuIndex* p,
+        idx_t n,
+        const float* x,
+        idx_t k,
+        const idx_t* assign,
+        const float* cdis,
+        float* D,
+        idx_t* I) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->search_preassigned(n, x, k, assign, cdis, D, I);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFFlat_new(
+        FaissGpuIndex** p,
+        FaissStandardGpuResources* r,
+        int d,
+        idx_t nlist,
+        FaissMetricType metric,
+        int device) {
+    try {
+        GpuIndexIVFConfig c;
+        c.device = device;
+        auto res = RES(r);
+        auto* h = new FaissIndex_H();
+        h->res = res;
+        h->index = new GpuIndexIVFFlat(res, d, nlist, MT(metric), c);
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- GpuIndexIVFPQ
+int faiss_GpuIndexIVFPQ_new(
+        FaissGpuIndex** p,
+        FaissStandardGpuResources* r,
+        int d,
+        idx_t nlist,
+        idx_t M,
+        idx_t nbits,
+        FaissMetricType metric,
+        int device) {
+    try {
+        GpuIndexIVFPQConfig c;
+        c.device = device;
+        auto res = RES(r);
+        auto* h = new FaissIndex_H();
+        h->res = res;
+        h->index = new GpuIndexIVFPQ(res, d, nlist, M, nbits, MT(metric), c);
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFPQ_setPQCentroids(FaissGpuIndex* p, const float* c) {
+    try {
+        AS<GpuIndexIVFPQ>(p, "GpuIndexIVFPQ")->setPQCentroids(c);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFPQ_getPQCentroids(const FaissGpuIndex* p, float* out) {
+    try {
+        AS<GpuIndexIVFPQ>(p, "GpuIndexIVFPQ")->getPQCentroids(out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFPQ_set_pq_clustering(FaissGpuIndex* p, int niter, int seed, int maxppc) {
+    try {
+        auto* i = AS<GpuIndexIVFPQ>(p, "GpuIndexIVFPQ");
+        if (niter > 0)
+            i->pq_cp.niter = niter;
+        if (seed >= 0)
+            i->pq_cp.seed = seed;
+        if (maxppc > 0)
+            i->pq_cp.max_points_per_centroid = maxppc;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFPQ_setPrecomputedCodes(FaissGpuIndex* p, int enable) {
+    try {
+        AS<GpuIndexIVFPQ>(p, "GpuIndexIVFPQ")->setPrecomputedCodes(enable != 0);
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- IndexShards
+int faiss_IndexShards_new(FaissIndexShards** p, idx_t d) {
+    return faiss_IndexShards_new_with_options(p, d, 0, 1);
+}
+int faiss_IndexShards_new_with_options(FaissIndexShards** p, idx_t d, int threaded, int successive_ids) {
+    try {
+        auto* h = new FaissIndex_H();
+        h->index = new IndexShards((int)d, threaded != 0, successive_ids != 0);
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_IndexShards_add_shard(FaissIndexShards* p, FaissIndex* shard) {
+    try {
+        AS<IndexShards>(p, "IndexShards")->add_shard(IX(shard));
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_IndexShards_remove_shard(FaissIndexShards* p, FaissIndex* shard) {
+    try {
+        AS<IndexShards>(p, "IndexShards")->remove_shard(IX(shard));
+    }
+    CATCH_AND_HANDLE
+}
+FaissIndex* faiss_IndexShards_at(FaissIndexShards*, int) {
+    // handles are owned by the caller; the C++ object can be reached through the shard handles
+    return nullptr;
+}
+int faiss_IndexShards_own_indices(const FaissIndexShards* p) {
+    auto* s = p ? dynamic_cast<IndexShards*>(p->index) : nullptr;
+    return s ? (int)s->own_indices : 0;
+}
+void faiss_IndexShards_set_own_indices(FaissIndexShards* p, int v) {
+    // ownership of sub-indexes stays with their C handles; refuse to double-free
+    (void)p;
+    (void)v;
+}
+int faiss_IndexShards_successive_ids(const FaissIndexShards* p) {
+    auto* s = p ? dynamic_cast<IndexShards*>(p->index) : nullptr;
+    return s ? (int)s->successive_ids : 0;
+}
+void faiss_IndexShards_set_successive_ids(FaissIndexShards* p, int v) {
+    auto* s = p ? dynamic_cast<IndexShards*>(p->index) : nullptr;
+    if (s)
+        s->successive_ids = v != 0;
+}
+
+// ---------------------------------------------------------------- clustering
+int faiss_b200_kmeans(
+        FaissStandardGpuResources* r,
+        int device,
+        size_t d,
+        size_t n,
+        size_t k,
+        const float* x,
+        int niter,
+        int seed,
+        int maxppc,
+        float* centroids_out,
+        float* obj_out) {
+    try {
+        auto res = RES(r);
+        ClusteringParameters cp;
+        if (niter > 0)
+            cp.niter = niter;
+        if (seed >= 0)
+            cp.seed = seed;
+        if (maxppc > 0)
+            cp.max_points_per_centroid = maxppc;
+        Clustering clus((int)d, (int)k, cp);
+        GpuIndexFlatConfig fc;
+        fc.device = device;
+        GpuIndexFlatL2 index(res, (int)d, fc);
+        clus.train((idx_t)n, x, index);
+        memcpy(centroids_out, clus.centroids.data(), sizeof(float) * d * k);
+        if (obj_out) {
+            for (size_t i = 0; i < clus.iteration_stats.size() && (int)i < cp.niter; i++)
+                obj_out[i] = clus.iteration_stats[i].obj;
+        }
+    }
+    CATCH_AND_HANDLE
+}
+
+// ---------------------------------------------------------------- tier 2 seams
+int b200_l2_norms(FaissStandardGpuResources* r, int device, const float* x, idx_t n, int d, float* norms) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        runL2Norms(x, n, d, norms, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_flat_search_exact(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* Y,
+        idx_t N,
+        int d,
+        const float* Q,
+        idx_t nq,
+        int k,
+        FaissMetricType metric,
+        float* D,
+        idx_t* I) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        FB_THROW_IF_NOT(k >= 1 && k <= kMaxK);
+        runFlatExact(res.get(), device, Q, nq, Y, N, d, k, MT(metric), 0, D, I, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_topk_merge(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* D_in,
+        const idx_t* I_in,
+        idx_t nq,
+        int nshard,
+        int k_in,
+        const idx_t* id_offsets,
+        int k,
+        FaissMetricType metric,
+        float* D,
+        idx_t* I) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        FB_THROW_IF_NOT(k >= 1 && k <= kMaxK);
+        runMergeTopK(D_in, I_in, nq, nshard, k_in, id_offsets, k, MT(metric), D, I, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_flat_tc_scores_debug(
+        FaissStandardGpuResources* r,
+        int device,
+        const void* Q16,
+        idx_t nq,
+        const void* Y16,
+        idx_t N,
+        int dpad,
+        float* S) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        runFlatTcScoresDebug((const __half*)Q16, nq, (const __half*)Y16, N, dpad, S, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_pq_encode(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* resid,
+        idx_t n,
+        int d,
+        int M,
+        const float* pq,
+        uint8_t* codes) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        runPQEncode(resid, n, d, M, 256, pq, codes, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_kmeans_update(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* x,
+        const idx_t* assign,
+        idx_t n,
+        int d,
+        idx_t k,
+        float* sums,
+        float* counts,
+        float* centroids) {
+    try {
+        auto res = RES(r);
+        DeviceScope s(device);
+        auto st = res->getDefaultStream(device);
+        runKmeansAccumulate(x, assign, n, d, k, sums, counts, st);
+        if (centroids)
+            runKmeansFinalize(sums, counts, k, d, centroids, st);
+    }
+    CATCH_AND_HANDLE
+}
+
+} // extern "C"

@@ -81,10 +81,16 @@ class FaissException : public std::exception {
 
 #define CUDA_CHECK_LAST() CUDA_VERIFY(cudaGetLastError())
 
-inline int64_t ceil_div(int64_t a, int64_t b) {
+#ifdef __CUDACC__
+#define FB_HD __host__ __device__
+#else
+#define FB_HD
+#endif
+
+FB_HD inline int64_t ceil_div(int64_t a, int64_t b) {
     return (a + b - 1) / b;
 }
-inline int64_t round_up(int64_t a, int64_t b) {
+FB_HD inline int64_t round_up(int64_t a, int64_t b) {
     return ceil_div(a, b) * b;
 }
 inline int next_pow2(int v) {

@@ -1,0 +1,954 @@
+// faiss_b200 -- Flat L2/IP k-NN on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces, for the Flat path, the reference chain
+//   runDistance<float> (faiss/gpu/impl/Distance.cu:121-405) = cuBLAS SGEMM -> fp32 tile in HBM ->
+//   l2SelectMinK (faiss/gpu/impl/L2Select.cu:137-187) -> blockSelectPair second level.
+//
+// Design (see DESIGN.md "Flat"):
+//   * Scoring.  score(q,y) = q.y - ||y||^2/2 (L2; maximise) or q.y (IP).  q and y are rounded to
+//     fp16 after a power-of-two scaling; the dot product runs on tcgen05.mma (kind::f16, fp32
+//     accumulate in TMEM).  |approx - exact| <= eps_q, a rigorous bound from the fp16 rounding
+//     model (10 mantissa bits) and the fp32 accumulation.
+//   * Fused filter.  A persistent warp-specialised kernel: warp 0 = TMA producer (query tile once
+//     per work unit, database tiles through a multi-stage mbarrier ring), warp 1 = single-thread
+//     MMA issuer (128x128xK tiles, 4 TMEM accumulator stages), warps 2..9 = epilogue: each thread
+//     owns ONE query row (a TMEM lane) and 64 of the tile's 128 columns; it pulls 32 columns at a
+//     time with tcgen05.ld, adds the per-column bias, and compares the chunk maximum against the
+//     query's threshold held in a register.  Scores never reach HBM; only the rare survivors are
+//     appended (plain stores, no atomics) to a thread-private candidate segment.
+//   * Thresholds come from geometric rounds over a pseudo-randomly permuted tile order: round r
+//     scans 3x the rows seen so far; after each round a small kernel folds the new candidates into
+//     a per-query sorted base list and sets threshold = (k-th best approx score) - 2*eps_q, which
+//     provably keeps every true top-k member.
+//   * Certified exact result.  The final kernel re-ranks the base list with the library's canonical
+//     fp32 arithmetic (same expression and order as flat_exact.cu) and sorts by (distance, id).
+//     Queries whose certificate fails (candidate segment or base list overflow) are recomputed by
+//     the exact SIMT kernel -- correctness never depends on the data distribution.
+#include <cuda_fp16.h>
+
+#include <cfloat>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+#include "select.cuh"
+#include "tc_ptx.cuh"
+
+namespace fb200 {
+
+void runMergeTopKKeyspace(
+        const float*, const idx_t*, int64_t, int, int, int, MetricType, int64_t, float*, idx_t*, cudaStream_t);
+
+namespace {
+
+constexpr int kTileM = 128;       // queries per tile (TMEM lanes)
+constexpr int kTileN = 128;       // database rows per tile (TMEM columns per accumulator stage)
+constexpr int kAccStages = 4;     // 4 x 128 columns = 512 TMEM columns
+constexpr int kKBlock = 64;       // fp16 elements per 128-byte swizzle row
+constexpr int kKBlockBytes = kTileN * kKBlock * 2; // 16 KiB per (128 rows x 64 halfs)
+constexpr int kThreads = 320;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kMaxYStages = 6;
+
+struct TcParams {
+    int numUnits;
+    int slices;
+    int tileBegin;      // permuted position range of this round
+    int tileEnd;
+    int tilesPerSlice;
+    unsigned long long permA, permB, numTiles;
+    int KB;             // dpad / 64
+    int yStages;
+    const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
+    const float* bias;  // [numTiles*128], -inf padded
+    const float* thr;   // [nq]  pass if score > thr
+    uint2* cand;        // [numUnits*256][cap] (score bits, row)
+    int cap;
+    int* candCount;     // [numUnits*256]
+    float* dump;        // debug: raw accumulators [nq][dumpLd]
+    long long dumpLd;
+    int nq;
+};
+
+__device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
+    return (int)(((unsigned long long)pos * p.permA + p.permB) % p.numTiles);
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
+        const __grid_constant__ CUtensorMap mapQ,
+        const __grid_constant__ CUtensorMap mapY,
+        const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte aligned carve-up (SWIZZLE_128B atoms need it)
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+            (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int stageBytes = p.KB * kKBlockBytes;
+    unsigned char* sQ = smem;
+    unsigned char* sY = smem + stageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sY + (size_t)p.yStages * stageBytes);
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* y_full = bars + 2;
+    uint64_t* y_empty = y_full + kMaxYStages;
+    uint64_t* t_full = y_empty + kMaxYStages;
+    uint64_t* t_empty = t_full + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&mapQ);
+        ptx::prefetch_tensormap(&mapY);
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 1);
+        for (int i = 0; i < p.yStages; i++) {
+            ptx::mbar_init(&y_full[i], 1);
+            ptx::mbar_init(&y_empty[i], 1);
+        }
+        for (int i = 0; i < kAccStages; i++) {
+            ptx::mbar_init(&t_full[i], 1);
+            ptx::mbar_init(&t_empty[i], kEpiWarps);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<512>(tmem_slot);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int ys = 0;
+            uint32_t yphase = 0;
+            int it = 0;
+            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
+                const int qt = u / p.slices;
+                const int sl = u % p.slices;
+                ptx::mbar_wait(q_empty, (it & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(q_full, (uint32_t)stageBytes);
+                ptx::tma_load_3d(sQ, &mapQ, q_full, 0, qt * kTileM, 0);
+                const int pb = p.tileBegin + sl * p.tilesPerSlice;
+                const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
+                for (int pp = pb; pp < pe; pp++) {
+                    const int t = perm_tile(p, pp);
+                    ptx::mbar_wait(&y_empty[ys], yphase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&y_full[ys], (uint32_t)stageBytes);
+                    ptx::tma_load_3d(sY + (size_t)ys * stageBytes, &mapY, &y_full[ys], 0, t * kTileN, 0);
+                    if (++ys == p.yStages) {
+                        ys = 0;
+                        yphase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
+            int ys = 0, as = 0;
+            uint32_t yphase = 0, aphase = 0;
+            int it = 0;
+            const uint32_t sQaddr = ptx::smem_u32(sQ);
+            const uint32_t sYaddr = ptx::smem_u32(sY);
+            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
+                const int sl = u % p.slices;
+                const int pb = p.tileBegin + sl * p.tilesPerSlice;
+                const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
+                ptx::mbar_wait(q_full, it & 1);
+                ptx::tc_fence_after();
+                for (int pp = pb; pp < pe; pp++) {
+                    ptx::mbar_wait(&t_empty[as], aphase ^ 1);
+                    ptx::mbar_wait(&y_full[ys], yphase);
+                    ptx::tc_fence_after();
+                    const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
+                    const uint32_t dcol = tmem_base + (uint32_t)as * kTileN;
+                    for (int kb = 0; kb < p.KB; kb++) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; k4++) {
+                            uint64_t da = ptx::make_smem_desc_sw128(sQaddr + kb * kKBlockBytes + k4 * 32);
+                            uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * kKBlockBytes + k4 * 32);
+                            ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        }
+                    }
+                    ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
+                    ptx::mma_commit(&t_full[as]);  // accumulator stage ready for the epilogue
+                    if (++ys == p.yStages) {
+                        ys = 0;
+                        yphase ^= 1;
+                    }
+                    if (++as == kAccStages) {
+                        as = 0;
+                        aphase ^= 1;
+                    }
+                }
+                ptx::mma_commit(q_empty); // query tile may be overwritten
+            }
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // which 64 columns of the tile
+        const int row = quarter * 32 + lane;
+        const float inv = *p.invScalePtr;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
+            const int qt = u / p.slices;
+            const int sl = u % p.slices;
+            const int q = qt * kTileM + row;
+            const float thr = (!DUMP && q < p.nq) ? p.thr[q] : CUDART_INF_F;
+            const long long seg = ((long long)u * kTileM + row) * 2 + half;
+            uint2* buf = p.cand + seg * p.cap;
+            int cnt = 0;
+            const int pb = p.tileBegin + sl * p.tilesPerSlice;
+            const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
+            for (int pp = pb; pp < pe; pp++) {
+                const int t = perm_tile(p, pp);
+                ptx::mbar_wait(&t_full[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 2; c++) {
+                    const int col0 = half * 64 + c * 32;
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(
+                            tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kTileN + col0), r);
+                    float b[32];
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)t * kTileN + col0);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 v = __ldg(bp + j);
+                        b[4 * j + 0] = v.x;
+                        b[4 * j + 1] = v.y;
+                        b[4 * j + 2] = v.z;
+                        b[4 * j + 3] = v.w;
+                    }
+                    ptx::tmem_ld_wait();
+                    if (DUMP) {
+                        if (q < p.nq) {
+                            float* dst = p.dump + (long long)q * p.dumpLd + (long long)t * kTileN + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                dst[j] = __uint_as_float(r[j]);
+                        }
+                    } else {
+                        float m = -CUDART_INF_F;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            b[j] = fmaf(__uint_as_float(r[j]), inv, b[j]);
+                            m = fmaxf(m, b[j]);
+                        }
+                        if (m > thr) {
+                            const unsigned rowBase = (unsigned)t * kTileN + col0;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (b[j] > thr) {
+                                    if (cnt < p.cap)
+                                        buf[cnt] = make_uint2(__float_as_uint(b[j]), rowBase + j);
+                                    cnt++;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    ptx::mbar_arrive(&t_empty[as]);
+                if (++as == kAccStages) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+            if (!DUMP)
+                p.candCount[seg] = cnt;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t count, float* out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = fabsf(x[i]);
+        if (v == v && v <= FLT_MAX) // ignore NaN / inf for the scale
+            m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f)
+        atomicMax(reinterpret_cast<int*>(out), __float_as_int(m)); // non-negative floats order as ints
+}
+
+// rows -> fp16 (scaled, zero padded to dpad) + bias + norms ; one warp per row
+__global__ void tc_prepare_rows_kernel(
+        const float* __restrict__ Y,
+        int64_t n,
+        int d,
+        int dpad,
+        float scale,
+        int isL2,
+        __half* __restrict__ Y16,
+        float* __restrict__ bias,
+        float* __restrict__ norms) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n)
+        return;
+    const float* src = Y + row * d;
+    __half* dst = Y16 + row * dpad;
+    float acc = 0.f;
+    for (int i = lane_id(); i < dpad; i += 32) {
+        float v = i < d ? src[i] : 0.f;
+        acc = fmaf(v, v, acc);
+        dst[i] = __float2half_rn(v * scale);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(kFullMask, acc, o);
+    if (lane_id() == 0) {
+        if (norms)
+            norms[row] = acc;
+        if (bias)
+            bias[row] = isL2 ? -0.5f * acc : 0.f;
+    }
+}
+
+// per-batch query preparation: power-of-two scale from absmax, fp16 conversion, eps, 1/(sq*sy)
+__global__ void tc_query_scale_kernel(const float* absmax, float yScale, float* qScaleOut, float* invOut) {
+    float m = *absmax;
+    float s = 1.f;
+    if (m > 0.f) {
+        int e;
+        frexpf(m, &e);           // m = f * 2^e, f in [0.5,1)
+        s = ldexpf(1.f, 14 - e); // m*s in [2^13, 2^14)
+    }
+    *qScaleOut = s;
+    *invOut = 1.f / (s * yScale);
+}
+
+__global__ void tc_prepare_queries_kernel(
+        const float* __restrict__ Q,
+        int64_t nq,
+        int d,
+        int dpad,
+        const float* __restrict__ qScale,
+        float c1,
+        float c2,
+        float yMaxNorm,
+        __half* __restrict__ Q16,
+        float* __restrict__ eps,
+        float* __restrict__ thr) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nq)
+        return;
+    const float scale = *qScale;
+    const float* src = Q + row * d;
+    __half* dst = Q16 + row * dpad;
+    float acc = 0.f;
+    for (int i = lane_id(); i < dpad; i += 32) {
+        float v = i < d ? src[i] : 0.f;
+        acc = fmaf(v, v, acc);
+        dst[i] = __float2half_rn(v * scale);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_xor_sync(kFullMask, acc, o);
+    if (lane_id() == 0) {
+        float qn = sqrtf(acc) * 1.0001f;
+        // |approx - exact| <= c1*|q||y| + c2*(|y|^2/2 + |q||y|)   (error model)
+        eps[row] = c1 * qn * yMaxNorm + c2 * (0.5f * yMaxNorm * yMaxNorm + qn * yMaxNorm);
+        thr[row] = -CUDART_INF_F;
+    }
+}
+
+// Fold this round's candidate segments into the per-query base list; set the new threshold.
+//   base lists hold (key = -score, id = row) sorted ascending; sentinel = (+inf, INT_MAX)
+__global__ void tc_select_kernel(
+        int nq,
+        int k,
+        int LIST,
+        int slices,
+        const uint2* __restrict__ cand,
+        int cap,
+        const int* __restrict__ candCount,
+        const float* __restrict__ eps,
+        float* __restrict__ baseKey, // [nq][LIST]
+        int* __restrict__ baseId,    // [nq][LIST]
+        float* __restrict__ thr,
+        int* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+    const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq)
+        return;
+    constexpr int BUF = 64;
+    unsigned char* base = smem_raw + SmemTopK<int>::bytes(LIST, BUF) * warp;
+    WarpTopK<int> w;
+    w.init(reinterpret_cast<float*>(base), reinterpret_cast<int*>(base + sizeof(float) * (LIST + BUF)), LIST, BUF, LIST);
+    // note: selection keeps the LIST best (k = LIST for the queue threshold)
+    const float* bk = baseKey + (int64_t)q * LIST;
+    const int* bi = baseId + (int64_t)q * LIST;
+    for (int e0 = 0; e0 < LIST; e0 += 32) {
+        int id = bi[e0 + lane];
+        w.add(id != IdLimits<int>::max(), bk[e0 + lane], id);
+    }
+    int overflow = 0;
+    const int qt = q / kTileM, row = q % kTileM;
+    for (int s = 0; s < slices; s++) {
+        const int u = qt * slices + s;
+        for (int h = 0; h < 2; h++) {
+            const long long seg = ((long long)u * kTileM + row) * 2 + h;
+            int c = candCount[seg];
+            if (c > cap) {
+                overflow = 1;
+                c = cap;
+            }
+            const uint2* sp = cand + seg * cap;
+            for (int e0 = 0; e0 < c; e0 += 32) {
+                int e = e0 + lane;
+                uint2 v = e < c ? sp[e] : make_uint2(0, 0);
+                w.add(e < c, -__uint_as_float(v.x), (int)v.y);
+            }
+        }
+    }
+    w.finish();
+    // k-th best approximate score -> threshold
+    float kthKey = w.q.keys[k - 1];
+    int kthId = w.q.ids[k - 1];
+    float t = -CUDART_INF_F;
+    if (kthId != IdLimits<int>::max()) {
+        float s = -kthKey - 2.f * eps[q];
+        t = nextafterf(s, -CUDART_INF_F);
+    }
+    // saturated list: an entry we could not keep might have been >= t
+    float lastKey = w.q.keys[LIST - 1];
+    int lastId = w.q.ids[LIST - 1];
+    if (lastId != IdLimits<int>::max() && -lastKey > t)
+        overflow = 1;
+    float* ok = baseKey + (int64_t)q * LIST;
+    int* oi = baseId + (int64_t)q * LIST;
+    for (int j = lane; j < LIST; j += 32) {
+        float key = w.q.keys[j];
+        int id = w.q.ids[j];
+        bool keep = id != IdLimits<int>::max() && (-key > t);
+        ok[j] = keep ? key : CUDART_INF_F;
+        oi[j] = keep ? id : IdLimits<int>::max();
+    }
+    if (lane == 0) {
+        thr[q] = t;
+        if (overflow)
+            flags[q] = 1;
+    }
+}
+
+// exact re-rank of the base list with the canonical fp32 arithmetic; output sorted by (dist, id)
+template <bool IS_L2>
+__global__ void tc_rerank_kernel(
+        int nq,
+        int d,
+        int k,
+        int LIST,
+        int KL, // output list size (pow2 >= k, >= 64)
+        const float* __restrict__ Q,
+        const float* __restrict__ Y,
+        const int* __restrict__ baseId,
+        float* __restrict__ outD,
+        idx_t* __restrict__ outI) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+    const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq)
+        return;
+    constexpr int BUF = 64;
+    unsigned char* base = smem_raw + SmemTopK<int>::bytes(KL, BUF) * warp;
+    WarpTopK<int> w;
+    w.init(reinterpret_cast<float*>(base), reinterpret_cast<int*>(base + sizeof(float) * (KL + BUF)), KL, BUF, k);
+    const float* qp = Q + (int64_t)q * d;
+    const int* bi = baseId + (int64_t)q * LIST;
+    for (int e0 = 0; e0 < LIST; e0 += 32) {
+        int id = bi[e0 + lane];
+        bool valid = id != IdLimits<int>::max();
+        float acc = 0.f;
+        if (valid) {
+            const float* yp = Y + (int64_t)id * d;
+            for (int i = 0; i < d; i++) {
+                float a = qp[i], b = yp[i];
+                if (IS_L2) {
+                    float df = a - b;
+                    acc = fmaf(df, df, acc);
+                } else {
+                    acc = fmaf(a, b, acc);
+                }
+            }
+            if (!IS_L2)
+                acc = -acc;
+        }
+        // the base list is sorted by approximate score, sentinels at the end
+        if (!__any_sync(kFullMask, valid))
+            break;
+        w.add(valid, acc, id);
+    }
+    w.finish();
+    for (int j = lane; j < k; j += 32) {
+        int id = w.q.ids[j];
+        bool ok = id != IdLimits<int>::max();
+        float key = w.q.keys[j];
+        outD[(int64_t)q * k + j] = ok ? (IS_L2 ? key : -key) : (IS_L2 ? FLT_MAX : -FLT_MAX);
+        outI[(int64_t)q * k + j] = ok ? (idx_t)id : -1;
+    }
+}
+
+__global__ void tc_init_base_kernel(float* baseKey, int* baseId, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        baseKey[i] = CUDART_INF_F;
+        baseId[i] = IdLimits<int>::max();
+    }
+}
+
+// compact flagged query indices: list[0..count)
+__global__ void tc_collect_flags_kernel(const int* flags, int nq, int* list, int* count) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && flags[q]) {
+        int pos = atomicAdd(count, 1);
+        list[pos] = q;
+    }
+}
+__global__ void tc_gather_queries_kernel(const float* Q, const int* list, int d, float* out) {
+    int i = blockIdx.x;
+    int q = list[i];
+    for (int j = threadIdx.x; j < d; j += blockDim.x)
+        out[(int64_t)i * d + j] = Q[(int64_t)q * d + j];
+}
+__global__ void tc_scatter_results_kernel(
+        const float* D,
+        const idx_t* I,
+        const int* list,
+        int k,
+        float* outD,
+        idx_t* outI) {
+    int i = blockIdx.x;
+    int q = list[i];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        outD[(int64_t)q * k + j] = D[(int64_t)i * k + j];
+        outI[(int64_t)q * k + j] = I[(int64_t)i * k + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(
+        CUtensorMap*,
+        CUtensorMapDataType,
+        cuuint32_t,
+        void*,
+        const cuuint64_t*,
+        const cuuint64_t*,
+        const cuuint32_t*,
+        const cuuint32_t*,
+        CUtensorMapInterleave,
+        CUtensorMapSwizzle,
+        CUtensorMapL2promotion,
+        CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled getEncodeTiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (err == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    FB_THROW_IF_NOT_MSG(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    return fn;
+}
+
+// fp16 matrix [rows][dpad] viewed as (64, rows, dpad/64); one box = (64, 128, dpad/64) = a full
+// K-extent tile laid out [kblock][row][64] with the 128-byte swizzle the UMMA descriptors expect.
+CUtensorMap makeTileMap(const __half* base, int64_t rows, int dpad) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)kKBlock, (cuuint64_t)rows, (cuuint64_t)(dpad / kKBlock)};
+    cuuint64_t strides[2] = {(cuuint64_t)dpad * 2, (cuuint64_t)kKBlock * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)kTileN, (cuuint32_t)(dpad / kKBlock)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = getEncodeTiled()(
+            &m,
+            CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+            3,
+            const_cast<__half*>(base),
+            dims,
+            strides,
+            box,
+            estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FB_THROW_IF_NOT_FMT(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return m;
+}
+
+unsigned long long gcd64(unsigned long long a, unsigned long long b) {
+    while (b) {
+        unsigned long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+struct SmemPlan {
+    int yStages;
+    size_t bytes;
+};
+
+SmemPlan planSmem(int KB) {
+    const size_t stage = (size_t)KB * kKBlockBytes;
+    const size_t budget = 220 * 1024;
+    const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + stage /*Q*/;
+    int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
+    FB_THROW_IF_NOT_MSG(ys >= 2, "dimension too large for the tensor-core Flat kernel");
+    return {ys, fixed + ys * stage};
+}
+
+template <bool DUMP>
+void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
+    auto kern = flat_tc_kernel<DUMP>;
+    CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
+    CUDA_CHECK_LAST();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// public launchers
+// ------------------------------------------------------------------------------------------
+void runAbsMax(const float* x, int64_t count, float* out, cudaStream_t stream) {
+    if (count == 0)
+        return;
+    int blocks = (int)std::min<int64_t>(1184, ceil_div(count, 256));
+    absmax_kernel<<<blocks, 256, 0, stream>>>(x, count, out);
+    CUDA_CHECK_LAST();
+}
+
+void runMaxOf(const float* x, int64_t count, float* out, cudaStream_t stream) {
+    runAbsMax(x, count, out, stream);
+}
+
+void runFlatTcPrepareRows(
+        const float* Y,
+        int64_t n,
+        int d,
+        int dpad,
+        float scale,
+        MetricType metric,
+        __half* Y16,
+        float* bias,
+        float* norms,
+        cudaStream_t stream) {
+    if (n == 0)
+        return;
+    int warps = 8;
+    tc_prepare_rows_kernel<<<(unsigned)ceil_div(n, warps), warps * 32, 0, stream>>>(
+            Y, n, d, dpad, scale, metric == METRIC_L2 ? 1 : 0, Y16, bias, norms);
+    CUDA_CHECK_LAST();
+}
+
+bool flatTcSupported(int d, int k, int64_t n) {
+    int dpad = (int)round_up(d, kKBlock);
+    return dpad <= 256 && k >= 1 && k <= 512 && n >= 32768 && n < (int64_t(1) << 31) - 256;
+}
+
+void runFlatTcScoresDebug(
+        const __half* Q16,
+        int64_t nq,
+        const __half* Y16,
+        int64_t n,
+        int dpad,
+        float* S,
+        cudaStream_t stream) {
+    FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= 256);
+    const int KB = dpad / kKBlock;
+    SmemPlan sp = planSmem(KB);
+    CUtensorMap mq = makeTileMap(Q16, nq, dpad);
+    CUtensorMap my = makeTileMap(Y16, n, dpad);
+    const int64_t numTiles = ceil_div(n, kTileN);
+    const int64_t qTiles = ceil_div(nq, kTileM);
+    // bias (zeros) and scale (1.0) for the debug run
+    float* bias = nullptr;
+    float* one = nullptr;
+    CUDA_VERIFY(cudaMallocAsync(&bias, sizeof(float) * numTiles * kTileN, stream));
+    CUDA_VERIFY(cudaMemsetAsync(bias, 0, sizeof(float) * numTiles * kTileN, stream));
+    CUDA_VERIFY(cudaMallocAsync(&one, sizeof(float), stream));
+    float h1 = 1.f;
+    CUDA_VERIFY(cudaMemcpyAsync(one, &h1, sizeof(float), cudaMemcpyHostToDevice, stream));
+    TcParams p{};
+    p.slices = 1;
+    p.numUnits = (int)qTiles;
+    p.tileBegin = 0;
+    p.tileEnd = (int)numTiles;
+    p.tilesPerSlice = (int)numTiles;
+    p.permA = 1;
+    p.permB = 0;
+    p.numTiles = (unsigned long long)numTiles;
+    p.KB = KB;
+    p.yStages = sp.yStages;
+    p.invScalePtr = one;
+    p.bias = bias;
+    p.thr = nullptr;
+    p.cand = nullptr;
+    p.cap = 0;
+    p.candCount = nullptr;
+    p.dump = S;
+    p.dumpLd = numTiles * kTileN; // S must be [nq][numTiles*128]
+    p.nq = (int)nq;
+    int dev = 0, sms = 0;
+    CUDA_VERIFY(cudaGetDevice(&dev));
+    CUDA_VERIFY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    launchTc<true>(mq, my, p, (int)std::min<int64_t>(p.numUnits, sms), sp.bytes, stream);
+    CUDA_VERIFY(cudaFreeAsync(bias, stream));
+    CUDA_VERIFY(cudaFreeAsync(one, stream));
+}
+
+void runFlatTcSearch(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nqAll,
+        const float* Y,
+        const __half* Y16,
+        const float* bias,
+        float yScale,
+        float yMaxNorm,
+        int64_t n,
+        int d,
+        int dpad,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream) {
+    if (nqAll == 0)
+        return;
+    FB_THROW_IF_NOT(flatTcSupported(d, k, n));
+    const int KB = dpad / kKBlock;
+    const SmemPlan sp = planSmem(KB);
+    const int sms = res->numSMs(device);
+    const int64_t T = ceil_div(n, kTileN);
+    const int LIST = std::max(128, next_pow2(2 * k));
+    const int KL = std::max(64, next_pow2(k));
+
+    // tile permutation: multiplicative hash with a multiplier coprime to T
+    unsigned long long A = (unsigned long long)((double)T * 0.6180339887498949);
+    if (A < 1)
+        A = 1;
+    while (gcd64(A, (unsigned long long)T) != 1)
+        A++;
+    const unsigned long long B = (unsigned long long)(T / 3);
+
+    // error model constants: fp16 rounding of both operands + fp32 accumulation slack
+    const float c1 = 1.01f * (ldexpf(1.f, -10) + (float)dpad * ldexpf(1.f, -22));
+    const float c2 = ldexpf(1.f, -22);
+
+    CUtensorMap mapY = makeTileMap(Y16, n, dpad);
+
+    const int64_t kQBatch = 16384; // queries per pass (bounds the candidate arena)
+    for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
+        const int64_t nq = std::min(kQBatch, nqAll - qb);
+        const float* Qb = Q + qb * d;
+        const int64_t qTiles = ceil_div(nq, kTileM);
+
+        auto q16 = res->temp(device, sizeof(__half) * qTiles * kTileM * dpad);
+        auto scal = res->temp(device, sizeof(float) * 4); // [absmax, qScale, inv, -]
+        auto eps = res->temp(device, sizeof(float) * nq);
+        auto thr = res->temp(device, sizeof(float) * nq);
+        auto flags = res->temp(device, sizeof(int) * (nq + 1));
+        auto baseKey = res->temp(device, sizeof(float) * nq * LIST);
+        auto baseId = res->temp(device, sizeof(int) * nq * LIST);
+
+        CUDA_VERIFY(cudaMemsetAsync(scal.data, 0, sizeof(float) * 4, stream));
+        CUDA_VERIFY(cudaMemsetAsync(flags.data, 0, sizeof(int) * (nq + 1), stream));
+        CUDA_VERIFY(cudaMemsetAsync(q16.data, 0, sizeof(__half) * qTiles * kTileM * dpad, stream));
+        float* sc = scal.as<float>();
+        runAbsMax(Qb, nq * d, sc + 0, stream);
+        tc_query_scale_kernel<<<1, 1, 0, stream>>>(sc + 0, yScale, sc + 1, sc + 2);
+        CUDA_CHECK_LAST();
+        tc_prepare_queries_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(
+                Qb, nq, d, dpad, sc + 1, c1, c2, yMaxNorm, q16.as<__half>(), eps.as<float>(), thr.as<float>());
+        CUDA_CHECK_LAST();
+        {
+            int64_t cnt = nq * LIST;
+            tc_init_base_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, stream>>>(
+                    baseKey.as<float>(), baseId.as<int>(), cnt);
+            CUDA_CHECK_LAST();
+        }
+        CUtensorMap mapQ = makeTileMap(q16.as<__half>(), qTiles * kTileM, dpad);
+
+        // ---- geometric rounds over the permuted tile order
+        struct Round {
+            int begin, end, slices, tilesPerSlice, cap;
+        };
+        std::vector<Round> rounds;
+        {
+            int64_t seen = 0;
+            while (seen < T) {
+                int64_t end = seen == 0 ? std::min<int64_t>(T, 32) : std::min<int64_t>(T, seen * 4);
+                if (T - end < end / 4)
+                    end = T; // do not leave a sliver for an extra round
+                int64_t tiles = end - seen;
+                // choose the slice count minimising (waves x tiles per slice)
+                int bestS = 1;
+                double bestCost = 1e300;
+                int64_t maxS = std::max<int64_t>(1, std::min<int64_t>(512, tiles / 8));
+                for (int64_t S = 1; S <= maxS; S++) {
+                    int64_t tps = ceil_div(tiles, S);
+                    int64_t units = qTiles * ceil_div(tiles, tps);
+                    int64_t waves = ceil_div(units, sms);
+                    double cost = (double)waves * (double)(tps + 6); // +6: per-unit fixed overhead
+                    if (cost < bestCost * 0.999) {
+                        bestCost = cost;
+                        bestS = (int)S;
+                    }
+                }
+                int64_t tps = ceil_div(tiles, bestS);
+                int S = (int)ceil_div(tiles, tps);
+                int cap;
+                if (seen == 0) {
+                    cap = (int)(tps * (kTileN / 2)); // everything passes in round 0
+                } else {
+                    double expect = 1.5 * k * ((double)tps / (double)seen) * 0.5;
+                    cap = next_pow2((int)std::min<double>(1 << 20, 4.0 * expect + 32.0));
+                    cap = std::max(cap, 32);
+                }
+                rounds.push_back({(int)seen, (int)end, S, (int)tps, cap});
+                seen = end;
+            }
+        }
+        size_t arenaBytes = 0, countBytes = 0;
+        for (auto& r : rounds) {
+            size_t units = (size_t)qTiles * r.slices;
+            arenaBytes = std::max(arenaBytes, units * 256 * (size_t)r.cap * sizeof(uint2));
+            countBytes = std::max(countBytes, units * 256 * sizeof(int));
+        }
+        auto arena = res->temp(device, arenaBytes);
+        auto counts = res->temp(device, countBytes);
+
+        const int selWarps = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / SmemTopK<int>::bytes(LIST, 64)));
+        const size_t selSmem = SmemTopK<int>::bytes(LIST, 64) * selWarps;
+        CUDA_VERIFY(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)selSmem));
+
+        for (auto& r : rounds) {
+            TcParams p{};
+            p.slices = r.slices;
+            p.numUnits = (int)(qTiles * r.slices);
+            p.tileBegin = r.begin;
+            p.tileEnd = r.end;
+            p.tilesPerSlice = r.tilesPerSlice;
+            p.permA = A;
+            p.permB = B;
+            p.numTiles = (unsigned long long)T;
+            p.KB = KB;
+            p.yStages = sp.yStages;
+            p.invScalePtr = sc + 2;
+            p.bias = bias;
+            p.thr = thr.as<float>();
+            p.cand = arena.as<uint2>();
+            p.cap = r.cap;
+            p.candCount = counts.as<int>();
+            p.dump = nullptr;
+            p.dumpLd = 0;
+            p.nq = (int)nq;
+            launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+            tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
+                    (int)nq,
+                    k,
+                    LIST,
+                    r.slices,
+                    arena.as<uint2>(),
+                    r.cap,
+                    counts.as<int>(),
+                    eps.as<float>(),
+                    baseKey.as<float>(),
+                    baseId.as<int>(),
+                    thr.as<float>(),
+                    flags.as<int>());
+            CUDA_CHECK_LAST();
+        }
+
+        // ---- exact re-rank
+        {
+            const int rrWarps = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / SmemTopK<int>::bytes(KL, 64)));
+            const size_t rrSmem = SmemTopK<int>::bytes(KL, 64) * rrWarps;
+            float* oD = outD + qb * k;
+            idx_t* oI = outI + qb * k;
+            if (metric == METRIC_L2) {
+                CUDA_VERIFY(cudaFuncSetAttribute(
+                        tc_rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrSmem));
+                tc_rerank_kernel<true><<<(unsigned)ceil_div(nq, rrWarps), rrWarps * 32, rrSmem, stream>>>(
+                        (int)nq, d, k, LIST, KL, Qb, Y, baseId.as<int>(), oD, oI);
+            } else {
+                CUDA_VERIFY(cudaFuncSetAttribute(
+                        tc_rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrSmem));
+                tc_rerank_kernel<false><<<(unsigned)ceil_div(nq, rrWarps), rrWarps * 32, rrSmem, stream>>>(
+                        (int)nq, d, k, LIST, KL, Qb, Y, baseId.as<int>(), oD, oI);
+            }
+            CUDA_CHECK_LAST();
+        }
+
+        // ---- certificate failures -> exact SIMT recompute
+        {
+            auto list = res->temp(device, sizeof(int) * nq);
+            int* countDev = flags.as<int>() + nq;
+            tc_collect_flags_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(
+                    flags.as<int>(), (int)nq, list.as<int>(), countDev);
+            CUDA_CHECK_LAST();
+            int nflag = 0;
+            CUDA_VERIFY(cudaMemcpyAsync(&nflag, countDev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+            if (nflag > 0) {
+                auto fq = res->temp(device, sizeof(float) * (size_t)nflag * d);
+                auto fD = res->temp(device, sizeof(float) * (size_t)nflag * k);
+                auto fI = res->temp(device, sizeof(idx_t) * (size_t)nflag * k);
+                tc_gather_queries_kernel<<<nflag, 128, 0, stream>>>(Qb, list.as<int>(), d, fq.as<float>());
+                CUDA_CHECK_LAST();
+                runFlatExact(res, device, fq.as<float>(), nflag, Y, n, d, k, metric, 0, fD.as<float>(), fI.as<idx_t>(), stream);
+                tc_scatter_results_kernel<<<nflag, 128, 0, stream>>>(
+                        fD.as<float>(), fI.as<idx_t>(), list.as<int>(), k, outD + qb * k, outI + qb * k);
+                CUDA_CHECK_LAST();
+                CUDA_VERIFY(cudaStreamSynchronize(stream));
+            }
+            lastFlatTcFallbacks() = nflag;
+        }
+    }
+}
+
+int& lastFlatTcFallbacks() {
+    static thread_local int v = 0;
+    return v;
+}
+
+} // namespace fb200

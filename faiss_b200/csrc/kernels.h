@@ -1,0 +1,246 @@
+// faiss_b200 -- launcher declarations for every device kernel (L1).  Host code (index objects,
+// C ABI) only sees these; all pointers are DEVICE pointers, all work is enqueued on `stream`.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "resources.h"
+
+namespace fb200 {
+
+// ---------------------------------------------------------------- flat_exact.cu
+// ||x||^2 per row (role of runL2Norm, faiss/gpu/impl/L2Norm.cu:176)
+void runL2Norms(const float* x, int64_t n, int d, float* norms, cudaStream_t stream);
+
+// Exact fp32 brute-force k-NN (SIMT, direct-form sum (q-y)^2 / sum q*y accumulated in dimension
+// order).  This is the always-correct path: small problems, odd dimensions, the fallback of the
+// tensor-core path, and the canonical arithmetic the tensor-core re-rank reproduces.
+// Role of runDistance<float> (faiss/gpu/impl/Distance.cu:121-405) with the k-select fused in.
+//   Q [nq,d], Y [n,d] row-major; outD [nq,k], outI [nq,k] (int64, row index + idBase; -1 missing)
+void runFlatExact(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        const float* Y,
+        int64_t n,
+        int d,
+        int k,
+        MetricType metric,
+        int64_t idBase,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+// k = 1 convenience (assignment): outI int64 [nq], outD optional
+void runFlatArgmin(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        const float* Y,
+        int64_t n,
+        int d,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+// Row-wise top-k over candidate lists (role of runBlockSelectPair / merge_knn_results,
+// faiss/gpu/utils/BlockSelectFloat.cu:98, faiss/utils/Heap.cpp:166-238).
+//   inD/inI: [rows, nlists, kin]; ids < 0 are skipped; idOffsets (optional, [nlists]) is added to
+//   ids of list l (IndexShards successive_ids translation, faiss/IndexShards.cpp:214-220).
+//   Keys are user-facing distances (L2: smaller better; IP: larger better).
+void runMergeTopK(
+        const float* inD,
+        const idx_t* inI,
+        int64_t rows,
+        int nlists,
+        int kin,
+        const idx_t* idOffsets,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+// residual x - c[assign] (NaN if assign = -1) ; role of runCalcResidual (VectorResidual.cu:26-176)
+void runCalcResidual(
+        const float* x,
+        const float* centroids,
+        const idx_t* assign,
+        int64_t n,
+        int d,
+        float* out,
+        cudaStream_t stream);
+// gather rows by id (reconstruct_batch) / by range
+void runGatherRows(const float* src, const idx_t* ids, int64_t n, int d, float* out, cudaStream_t stream);
+
+// ---------------------------------------------------------------- flat_tc.cu  (tcgen05 path)
+struct FlatTcPlan; // opaque: tensor maps + scratch sizing for one (index, nq, k) shape
+
+// fp32 rows -> scaled fp16 rows (padded to dpad, multiple of 64) + score bias; incremental (rows
+// [n0, n0+n) only).  bias[j] = -||y_j||^2/2 for L2, 0 for IP.
+void runFlatTcPrepareRows(
+        const float* Y,
+        int64_t n,
+        int d,
+        int dpad,
+        float scale,
+        MetricType metric,
+        __half* Y16,
+        float* bias,
+        float* norms,
+        cudaStream_t stream);
+
+// max |x| over a matrix (device scalar, float) -- used to pick the power-of-two fp16 scale
+void runAbsMax(const float* x, int64_t count, float* out /*device, must be zeroed*/, cudaStream_t stream);
+// max row norm^2
+void runMaxOf(const float* x, int64_t count, float* out /*device, zeroed; x >= 0*/, cudaStream_t stream);
+
+bool flatTcSupported(int d, int k, int64_t n);
+
+// Full certified search: fp16 tcgen05 scoring + candidate emission + exact fp32 re-rank, with the
+// exact SIMT kernel as fallback for queries whose certificate fails.  See flat_tc.cu.
+void runFlatTcSearch(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        const float* Y,      // fp32 rows [n,d] (exact re-rank)
+        const __half* Y16,   // fp16 scaled rows [n,dpad]
+        const float* bias,   // [n]
+        float yScale,        // power of two applied to Y16
+        float yMaxNorm,      // max ||y|| (unscaled)
+        int64_t n,
+        int d,
+        int dpad,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+// number of queries the last runFlatTcSearch on this thread recomputed with the exact kernel
+int& lastFlatTcFallbacks();
+
+// debug / unit-test seam: raw fp16 tensor-core score tile  S[nq,n] = Q16 . Y16^T  (fp32 out)
+void runFlatTcScoresDebug(
+        const __half* Q16,
+        int64_t nq,
+        const __half* Y16,
+        int64_t n,
+        int dpad,
+        float* S,
+        cudaStream_t stream);
+
+// ---------------------------------------------------------------- kmeans.cu
+// centroid update (role of compute_centroids, faiss/impl/ClusteringHelpers.cpp:101-172):
+// sums[c] += x_i for assign[i]=c, counts[c] += 1 ; then centroids = sums / counts
+void runKmeansAccumulate(
+        const float* x,
+        const idx_t* assign,
+        int64_t n,
+        int d,
+        int64_t k,
+        float* sums /*[k,d] zeroed*/,
+        float* counts /*[k] zeroed*/,
+        cudaStream_t stream);
+void runKmeansFinalize(
+        const float* sums,
+        const float* counts,
+        int64_t k,
+        int d,
+        float* centroids /* in: previous, out: new (unchanged where count==0) */,
+        cudaStream_t stream);
+
+// ---------------------------------------------------------------- ivf.cu
+// PQ encode: codes[i][m] = argmin_c || r_i[m*dsub:(m+1)*dsub] - pq[m][c] ||^2
+//   (role of IVFPQ::appendVectors_ per-subquantizer k=1 search, faiss/gpu/impl/IVFPQ.cu:129-257;
+//    arithmetic follows faiss/impl/ProductQuantizer.cpp compute_code: direct L2, first min wins)
+void runPQEncode(
+        const float* resid,
+        int64_t n,
+        int d,
+        int M,
+        int ksub,
+        const float* pqCentroids /*[M][ksub][dsub]*/,
+        uint8_t* codes /*[n][M]*/,
+        cudaStream_t stream);
+
+// histogram of list assignments + stable scatter positions (device-side append bookkeeping;
+// replaces the host unordered_map pass of IVFBase::addVectorsToLists_, IVFBase.cu:693-905)
+void runIvfCountAssign(const idx_t* assign, int64_t n, int64_t nlist, int* counts /*[nlist] += */, cudaStream_t stream);
+// offsets[i] = position of vector i inside its list (listLen[assign[i]] before this batch + rank of
+// i among batch vectors with the same list, in batch order)
+void runIvfAppendOffsets(
+        const idx_t* assign,
+        int64_t n,
+        int64_t nlist,
+        const int* listLenBefore /*[nlist]*/,
+        int* offsets /*[n]*/,
+        int* scratch /*[nlist]*/,
+        cudaStream_t stream);
+// scatter rows (codeSize bytes each) + ids to list storage: dst = base + listStart[l]*codeSize
+void runIvfScatter(
+        const uint8_t* rows,
+        const idx_t* ids,
+        const idx_t* assign,
+        const int* offsets,
+        int64_t n,
+        int codeSize,
+        const int64_t* listStart /*[nlist] element offset of each list in the arena*/,
+        uint8_t* arenaCodes,
+        idx_t* arenaIds,
+        cudaStream_t stream);
+
+// IVF-Flat list scan (role of runIVFInterleavedScan, faiss/gpu/impl/IVFInterleaved.cu:179).
+//   probes [nq,nprobe] list ids (-1 = skip), lists are row-major fp32 [len,d] inside the arena.
+void runIvfFlatScan(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        int d,
+        const idx_t* probes,
+        int nprobe,
+        const int64_t* listStart,
+        const int* listLen,
+        const float* arenaVecs,
+        const idx_t* arenaIds,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+// IVF-PQ list scan (role of runPQScanMultiPassNoPrecomputed + pqCodeDistances,
+// faiss/gpu/impl/PQScanMultiPassNoPrecomputed-inl.cuh:527, PQCodeDistances-inl.cuh:591): the
+// per-(query,list) LUT is built in shared memory, codes are streamed with 128-bit loads, the
+// running top-k stays on chip.  Distance form follows the reference CPU scanner
+// (faiss/impl/pq_code_distance/IVFPQ_QueryTables.cpp:126-192): L2 by_residual:
+//   dis = sum_m || (q - c_list)_m - pq[m][code_m] ||^2 ; IP: q.c_list + sum_m q_m . pq[m][code_m]
+void runIvfPqScan(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        int d,
+        const idx_t* probes,
+        const float* coarseDis,
+        int nprobe,
+        const float* coarseCentroids /*[nlist,d]*/,
+        const float* pqCentroids /*[M][ksub][dsub]*/,
+        int M,
+        const int64_t* listStart,
+        const int* listLen,
+        const uint8_t* arenaCodes,
+        const idx_t* arenaIds,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
+} // namespace fb200

@@ -1,0 +1,134 @@
+// faiss_b200 -- k-means centroid update on the device.
+//
+// The reference runs Lloyd's update on the CPU every iteration (compute_centroids,
+// faiss/impl/ClusteringHelpers.cpp:101-172: every OpenMP thread scans all n assignments) after
+// re-uploading the training set for the GPU assignment step.  Here the training set stays in HBM;
+// assignment is the Flat k=1 kernel and the update below is a privatised reduction:
+//   * small codebooks (k*d floats fit in shared memory, e.g. the 256 x dsub PQ codebooks): each
+//     block accumulates its slice of points into a shared-memory copy with shared atomics and
+//     flushes once with global RED;
+//   * large codebooks (IVF coarse centroids): one warp per point, lanes over dimensions, global
+//     RED.ADD.F32 (low contention: points hit k >= thousands of rows).
+#include "kernels.h"
+#include "select.cuh"
+
+namespace fb200 {
+
+__global__ void kmeans_accum_smem_kernel(
+        const float* __restrict__ x,
+        const idx_t* __restrict__ assign,
+        int64_t n,
+        int d,
+        int k,
+        int64_t pointsPerBlock,
+        float* __restrict__ sums,
+        float* __restrict__ counts) {
+    extern __shared__ float sm[]; // [k*d] sums + [k] counts
+    float* ssum = sm;
+    float* scnt = sm + (size_t)k * d;
+    for (int i = threadIdx.x; i < k * d + k; i += blockDim.x)
+        sm[i] = 0.f;
+    __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * pointsPerBlock;
+    const int64_t p1 = min(n, p0 + pointsPerBlock);
+    // flat element loop: element e of the slice = (point, dim)
+    for (int64_t e = p0 * d + threadIdx.x; e < p1 * d; e += blockDim.x) {
+        int64_t pt = e / d;
+        int j = (int)(e - pt * d);
+        idx_t c = assign[pt];
+        if (c >= 0 && c < k) {
+            atomicAdd(&ssum[c * d + j], x[e]);
+            if (j == 0)
+                atomicAdd(&scnt[c], 1.f);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+        float v = ssum[i];
+        if (v != 0.f)
+            atomicAdd(&sums[i], v);
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        float v = scnt[i];
+        if (v != 0.f)
+            atomicAdd(&counts[i], v);
+    }
+}
+
+__global__ void kmeans_accum_global_kernel(
+        const float* __restrict__ x,
+        const idx_t* __restrict__ assign,
+        int64_t n,
+        int d,
+        int64_t k,
+        float* __restrict__ sums,
+        float* __restrict__ counts) {
+    const int64_t pt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= n)
+        return;
+    const idx_t c = assign[pt];
+    if (c < 0 || c >= k)
+        return;
+    const float* xp = x + pt * d;
+    float* sp = sums + c * d;
+    for (int j = lane_id(); j < d; j += 32)
+        atomicAdd(&sp[j], xp[j]);
+    if (lane_id() == 0)
+        atomicAdd(&counts[c], 1.f);
+}
+
+void runKmeansAccumulate(
+        const float* x,
+        const idx_t* assign,
+        int64_t n,
+        int d,
+        int64_t k,
+        float* sums,
+        float* counts,
+        cudaStream_t stream) {
+    if (n == 0)
+        return;
+    size_t smem = sizeof(float) * ((size_t)k * d + k);
+    if (smem <= 64 * 1024) {
+        int64_t ppb = std::max<int64_t>(256, ceil_div(n, 148 * 4));
+        CUDA_VERIFY(cudaFuncSetAttribute(
+                kmeans_accum_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmeans_accum_smem_kernel<<<(unsigned)ceil_div(n, ppb), 256, smem, stream>>>(
+                x, assign, n, d, (int)k, ppb, sums, counts);
+    } else {
+        int warps = 8;
+        kmeans_accum_global_kernel<<<(unsigned)ceil_div(n, warps), warps * 32, 0, stream>>>(
+                x, assign, n, d, k, sums, counts);
+    }
+    CUDA_CHECK_LAST();
+}
+
+__global__ void kmeans_finalize_kernel(
+        const float* __restrict__ sums,
+        const float* __restrict__ counts,
+        int64_t k,
+        int d,
+        float* __restrict__ centroids) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * d)
+        return;
+    float c = counts[i / d];
+    if (c > 0.f) {
+        // faiss/impl/ClusteringHelpers.cpp:160-170: multiply by 1/count
+        float norm = 1.f / c;
+        centroids[i] = sums[i] * norm;
+    }
+}
+
+void runKmeansFinalize(
+        const float* sums,
+        const float* counts,
+        int64_t k,
+        int d,
+        float* centroids,
+        cudaStream_t stream) {
+    kmeans_finalize_kernel<<<(unsigned)ceil_div(k * d, 256), 256, 0, stream>>>(sums, counts, k, d, centroids);
+    CUDA_CHECK_LAST();
+}
+
+} // namespace fb200

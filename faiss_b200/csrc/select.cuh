@@ -60,7 +60,7 @@ struct SmemTopK {
     int BUF;
     int k;
 
-    __device__ __forceinline__ static size_t bytes(int LIST, int BUF) {
+    __host__ __device__ __forceinline__ static size_t bytes(int LIST, int BUF) {
         return size_t(LIST + BUF) * (sizeof(float) + sizeof(IdT));
     }
 

@@ -1,0 +1,165 @@
+/* faiss_b200 -- C ABI of the B200-native similarity-search backend.
+ *
+ * Plain C (extern "C"), opaque handles, plain pointers and sizes; no torch / C++ types.
+ * Two tiers:
+ *   (1) index-level entry points with the names, argument meaning and error convention of the
+ *       reference C API (c_api/Index_c.h:60-175, c_api/IndexShards_c.h:28-40,
+ *       c_api/IndexIVF_c.h:118-160, c_api/gpu/StandardGpuResources_c.h, c_api/error_c.h:19-35):
+ *       every function returns 0 on success, -2 for a Faiss-style exception (user error), -4 for a
+ *       standard C++ exception, -1 otherwise; the message is read with faiss_get_last_error().
+ *       The GPU index constructors, which the reference only exposes in C++
+ *       (faiss/gpu/GpuIndexFlat.h:43-64, GpuIndexIVFFlat.h:37-59, GpuIndexIVFPQ.h:56-82), are
+ *       exported here as faiss_GpuIndex*_new.
+ *   (2) kernel-level seams (b200_*): device pointers + the resources' ordering stream, mirroring
+ *       the reference's internal run* launchers.
+ *
+ * Pointer residency: for tier (1) every x / distances / labels / ids pointer may be host or
+ * device memory (faiss/gpu/GpuIndex.cu:373-448).  Tier (2) takes DEVICE pointers only.
+ * idx_t is int64_t (faiss/MetricType.h:52).
+ */
+#ifndef FAISS_B200_C_H
+#define FAISS_B200_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FB200_API __attribute__((visibility("default")))
+#else
+#define FB200_API
+#endif
+
+typedef int64_t idx_t;
+
+typedef enum FaissErrorCode { /* c_api/error_c.h:19-30 */
+    OK = 0,
+    UNKNOWN_EXCEPT = -1,
+    FAISS_EXCEPT = -2,
+    STD_EXCEPT = -4
+} FaissErrorCode;
+
+typedef enum FaissMetricType { /* c_api/Index_c.h:26-36 (subset on the hot path) */
+    METRIC_INNER_PRODUCT = 0,
+    METRIC_L2 = 1
+} FaissMetricType;
+
+typedef struct FaissIndex_H FaissIndex;                               /* c_api/Index_c.h:49 */
+typedef struct FaissIndex_H FaissGpuIndex;
+typedef struct FaissIndex_H FaissIndexShards;
+typedef struct FaissStandardGpuResources_H FaissStandardGpuResources; /* c_api/gpu/StandardGpuResources_c.h:24 */
+
+FB200_API const char* faiss_get_last_error(void);                    /* c_api/error_c.h:33 */
+FB200_API const char* faiss_b200_version(void);
+
+/* ---- StandardGpuResources (c_api/gpu/StandardGpuResources_c.h:24-55) ---- */
+FB200_API int faiss_StandardGpuResources_new(FaissStandardGpuResources** p_res);
+FB200_API void faiss_StandardGpuResources_free(FaissStandardGpuResources* res);
+FB200_API int faiss_StandardGpuResources_noTempMemory(FaissStandardGpuResources* res);
+FB200_API int faiss_StandardGpuResources_setTempMemory(FaissStandardGpuResources* res, size_t size);
+FB200_API int faiss_StandardGpuResources_setPinnedMemory(FaissStandardGpuResources* res, size_t size);
+FB200_API int faiss_StandardGpuResources_setDefaultStream(FaissStandardGpuResources* res, int device, void* cuda_stream);
+FB200_API int faiss_StandardGpuResources_setDefaultNullStreamAllDevices(FaissStandardGpuResources* res);
+/* c_api/gpu/GpuResources_c.h: getDefaultStream / syncDefaultStream */
+FB200_API int faiss_StandardGpuResources_getDefaultStream(FaissStandardGpuResources* res, int device, void** out_stream);
+FB200_API int faiss_StandardGpuResources_syncDefaultStream(FaissStandardGpuResources* res, int device);
+/* getMemoryInfo (faiss/gpu/StandardGpuResources.h:243): writes a JSON object {dev:{type:[count,bytes]}} */
+FB200_API int faiss_StandardGpuResources_getMemoryInfo(FaissStandardGpuResources* res, char* buf, size_t buflen);
+FB200_API int faiss_StandardGpuResources_getTempMemoryAvailable(FaissStandardGpuResources* res, int device, size_t* out);
+
+/* ---- generic Index (c_api/Index_c.h:49-175) ---- */
+FB200_API void faiss_Index_free(FaissIndex* index);
+FB200_API int faiss_Index_d(const FaissIndex* index);
+FB200_API int faiss_Index_is_trained(const FaissIndex* index);
+FB200_API idx_t faiss_Index_ntotal(const FaissIndex* index);
+FB200_API FaissMetricType faiss_Index_metric_type(const FaissIndex* index);
+FB200_API int faiss_Index_verbose(const FaissIndex* index);
+FB200_API void faiss_Index_set_verbose(FaissIndex* index, int v);
+FB200_API int faiss_Index_train(FaissIndex* index, idx_t n, const float* x);
+FB200_API int faiss_Index_add(FaissIndex* index, idx_t n, const float* x);
+FB200_API int faiss_Index_add_with_ids(FaissIndex* index, idx_t n, const float* x, const idx_t* xids);
+FB200_API int faiss_Index_search(const FaissIndex* index, idx_t n, const float* x, idx_t k, float* distances, idx_t* labels);
+FB200_API int faiss_Index_assign(FaissIndex* index, idx_t n, const float* x, idx_t* labels, idx_t k);
+FB200_API int faiss_Index_reset(FaissIndex* index);
+FB200_API int faiss_Index_reconstruct(const FaissIndex* index, idx_t key, float* recons);
+FB200_API int faiss_Index_reconstruct_n(const FaissIndex* index, idx_t i0, idx_t ni, float* recons);
+FB200_API int faiss_Index_reconstruct_batch(const FaissIndex* index, idx_t n, const idx_t* keys, float* recons);
+FB200_API int faiss_Index_compute_residual(const FaissIndex* index, const float* x, float* residual, idx_t key);
+FB200_API int faiss_Index_compute_residual_n(const FaissIndex* index, idx_t n, const float* x, float* residuals, const idx_t* keys);
+
+/* ---- GpuIndexFlat (faiss/gpu/GpuIndexFlat.h:43-217) ---- */
+/* use_tensor_cores: 1 = tcgen05 path when the shape supports it (default), 0 = exact SIMT only */
+FB200_API int faiss_GpuIndexFlat_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, FaissMetricType metric, int device, int use_tensor_cores);
+FB200_API int faiss_GpuIndexFlatL2_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, int device);
+FB200_API int faiss_GpuIndexFlatIP_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, int device);
+/* copyFrom / copyTo against the CPU IndexFlat payload (faiss/gpu/GpuIndexFlat.cu:105-176) */
+FB200_API int faiss_GpuIndexFlat_copyFrom(FaissGpuIndex* index, idx_t n, const float* xb);
+FB200_API int faiss_GpuIndexFlat_copyTo(const FaissGpuIndex* index, float* xb_out);
+FB200_API int faiss_GpuIndexFlat_setUseTensorCores(FaissGpuIndex* index, int enable);
+/* diagnostics of the last search on this index: out[0] = tensor-core path used, out[1] = queries
+   recomputed by the exact kernel because their certificate failed */
+FB200_API int faiss_GpuIndexFlat_lastSearchInfo(const FaissGpuIndex* index, int* out2);
+
+/* ---- GpuIndexIVF (faiss/gpu/GpuIndexIVF.h:40-167) ---- */
+FB200_API int faiss_GpuIndexIVF_set_nprobe(FaissGpuIndex* index, size_t nprobe);
+FB200_API size_t faiss_GpuIndexIVF_nprobe(const FaissGpuIndex* index);
+FB200_API size_t faiss_GpuIndexIVF_nlist(const FaissGpuIndex* index);
+FB200_API int faiss_GpuIndexIVF_set_clustering(FaissGpuIndex* index, int niter, int seed, int max_points_per_centroid);
+FB200_API int faiss_GpuIndexIVF_reserveMemory(FaissGpuIndex* index, size_t num_vecs);
+FB200_API int faiss_GpuIndexIVF_reclaimMemory(FaissGpuIndex* index, size_t* reclaimed);
+FB200_API size_t faiss_GpuIndexIVF_get_list_size(const FaissGpuIndex* index, size_t list_no); /* c_api/IndexIVF_c.h:129 */
+/* getListVectorData / getListIndices (faiss/gpu/GpuIndexIVF.h:120-130): host output buffers */
+FB200_API int faiss_GpuIndexIVF_getListVectorData(const FaissGpuIndex* index, size_t list_no, uint8_t* codes_out);
+FB200_API int faiss_GpuIndexIVF_getListIndices(const FaissGpuIndex* index, size_t list_no, idx_t* ids_out);
+/* copyFrom pieces (faiss/gpu/GpuIndexIVF.cu copyFrom, IVFBase.cu:328-451): coarse centroids and
+   ArrayInvertedLists-format lists */
+FB200_API int faiss_GpuIndexIVF_setCoarseCentroids(FaissGpuIndex* index, const float* centroids);
+FB200_API int faiss_GpuIndexIVF_getCoarseCentroids(const FaissGpuIndex* index, float* centroids_out);
+FB200_API int faiss_GpuIndexIVF_setList(FaissGpuIndex* index, size_t list_no, idx_t len, const uint8_t* codes, const idx_t* ids);
+FB200_API int faiss_GpuIndexIVF_set_is_trained(FaissGpuIndex* index, int v);
+/* c_api/IndexIVF_c.h:118 faiss_IndexIVF_search_preassigned */
+FB200_API int faiss_GpuIndexIVF_search_preassigned(const FaissGpuIndex* index, idx_t n, const float* x, idx_t k, const idx_t* assign, const float* centroid_dis, float* distances, idx_t* labels);
+
+FB200_API int faiss_GpuIndexIVFFlat_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, idx_t nlist, FaissMetricType metric, int device);
+
+/* ---- GpuIndexIVFPQ (faiss/gpu/GpuIndexIVFPQ.h:56-181) ---- */
+FB200_API int faiss_GpuIndexIVFPQ_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, idx_t nlist, idx_t M, idx_t nbits, FaissMetricType metric, int device);
+FB200_API int faiss_GpuIndexIVFPQ_setPQCentroids(FaissGpuIndex* index, const float* centroids /* [M][256][dsub] */);
+FB200_API int faiss_GpuIndexIVFPQ_getPQCentroids(const FaissGpuIndex* index, float* centroids_out);
+FB200_API int faiss_GpuIndexIVFPQ_set_pq_clustering(FaissGpuIndex* index, int niter, int seed, int max_points_per_centroid);
+FB200_API int faiss_GpuIndexIVFPQ_setPrecomputedCodes(FaissGpuIndex* index, int enable);
+
+/* ---- IndexShards (c_api/IndexShards_c.h:28-40) ---- */
+FB200_API int faiss_IndexShards_new(FaissIndexShards** p_index, idx_t d);
+FB200_API int faiss_IndexShards_new_with_options(FaissIndexShards** p_index, idx_t d, int threaded, int successive_ids);
+FB200_API int faiss_IndexShards_add_shard(FaissIndexShards* index, FaissIndex* shard);
+FB200_API int faiss_IndexShards_remove_shard(FaissIndexShards* index, FaissIndex* shard);
+FB200_API FaissIndex* faiss_IndexShards_at(FaissIndexShards* index, int i);
+FB200_API int faiss_IndexShards_own_indices(const FaissIndexShards* index);
+FB200_API void faiss_IndexShards_set_own_indices(FaissIndexShards* index, int v);
+FB200_API int faiss_IndexShards_successive_ids(const FaissIndexShards* index);
+FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int v);
+
+/* ---- Clustering (c_api/Clustering_c.h faiss_kmeans_clustering; faiss/Clustering.cpp:60-380) ----
+   Lloyd k-means with the training set resident on the device; x host or device. */
+FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, float* centroids_out /* host [k*d] */, float* obj_out /* host [niter] or NULL */);
+
+/* ================= tier 2: kernel seams, DEVICE pointers, enqueued on the default stream ======= */
+/* role of runL2Norm (faiss/gpu/impl/L2Norm.cu:176) */
+FB200_API int b200_l2_norms(FaissStandardGpuResources* res, int device, const float* x, idx_t n, int d, float* norms);
+/* role of bfKnnOnDevice (faiss/gpu/impl/Distance.cuh:300), exact SIMT arithmetic */
+FB200_API int b200_flat_search_exact(FaissStandardGpuResources* res, int device, const float* Y, idx_t N, int d, const float* Q, idx_t nq, int k, FaissMetricType metric, float* D, idx_t* I);
+/* role of merge_knn_results (faiss/utils/Heap.cpp:166-238) on the device: in [nq, nshard, k] */
+FB200_API int b200_topk_merge(FaissStandardGpuResources* res, int device, const float* D_in, const idx_t* I_in, idx_t nq, int nshard, int k_in, const idx_t* id_offsets /* device, [nshard] or NULL */, int k, FaissMetricType metric, float* D, idx_t* I);
+/* unit-test seam for the tcgen05 path: S[nq, roundup(N,128)] = Q16 . Y16^T (fp16 inputs) */
+FB200_API int b200_flat_tc_scores_debug(FaissStandardGpuResources* res, int device, const void* Q16, idx_t nq, const void* Y16, idx_t N, int dpad, float* S);
+FB200_API int b200_pq_encode(FaissStandardGpuResources* res, int device, const float* residuals, idx_t n, int d, int M, const float* pq_centroids, uint8_t* codes);
+FB200_API int b200_kmeans_update(FaissStandardGpuResources* res, int device, const float* x, const idx_t* assign, idx_t n, int d, idx_t k, float* sums, float* counts, float* centroids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
