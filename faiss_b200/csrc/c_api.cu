@@ -557,6 +557,36 @@ int faiss_b200_kmeans(
     CATCH_AND_HANDLE
 }
 
+// ---------------------------------------------------------------- host utilities
+int faiss_b200_rand_perm(int* perm, size_t n, int64_t seed) {
+    try {
+        fb200::rand_perm(perm, n, seed);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_b200_split_clusters(size_t d, size_t k, size_t n, float* hassign, float* centroids, int* nsplit_out) {
+    try {
+        int ns = fb200::split_clusters(d, k, n, hassign, centroids);
+        if (nsplit_out)
+            *nsplit_out = ns;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_b200_merge_knn_results_host(
+        idx_t n,
+        idx_t k,
+        int nshard,
+        FaissMetricType metric,
+        const float* all_distances,
+        const idx_t* all_labels,
+        float* distances,
+        idx_t* labels) {
+    try {
+        merge_knn_results_host(n, k, nshard, MT(metric), all_distances, all_labels, distances, labels);
+    }
+    CATCH_AND_HANDLE
+}
+
 // ---------------------------------------------------------------- tier 2 seams
 int b200_l2_norms(FaissStandardGpuResources* r, int device, const float* x, idx_t n, int d, float* norms) {
     try {

@@ -147,6 +147,13 @@ FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int
    Lloyd k-means with the training set resident on the device; x host or device. */
 FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, float* centroids_out /* host [k*d] */, float* obj_out /* host [niter] or NULL */);
 
+/* ---- host-side utilities of the path (no GPU needed) ----
+   rand_perm: faiss/utils/random.cpp:188-199; split_clusters: faiss/impl/ClusteringHelpers.cpp:177-240;
+   merge_knn_results: faiss/utils/Heap.cpp:166-238 (all_* laid out [nshard][n][k]) */
+FB200_API int faiss_b200_rand_perm(int* perm, size_t n, int64_t seed);
+FB200_API int faiss_b200_split_clusters(size_t d, size_t k, size_t n, float* hassign, float* centroids, int* nsplit_out);
+FB200_API int faiss_b200_merge_knn_results_host(idx_t n, idx_t k, int nshard, FaissMetricType metric, const float* all_distances, const idx_t* all_labels, float* distances, idx_t* labels);
+
 /* ================= tier 2: kernel seams, DEVICE pointers, enqueued on the default stream ======= */
 /* role of runL2Norm (faiss/gpu/impl/L2Norm.cu:176) */
 FB200_API int b200_l2_norms(FaissStandardGpuResources* res, int device, const float* x, idx_t n, int d, float* norms);

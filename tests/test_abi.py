@@ -1,0 +1,93 @@
+"""The C-ABI library loads and exports every symbol include/faiss_b200_c.h declares; host-side
+logic of the path (no GPU compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "faiss_b200_c.h")).read()
+    return sorted(s for s in set(re.findall(r"FB200_API\s+[^;(]*?\b(\w+)\s*\(", txt)) if s != "__attribute__")
+
+
+def test_header_declares_functions():
+    syms = _declared_symbols()
+    assert len(syms) > 50
+    for must in ("faiss_Index_search", "faiss_GpuIndexFlat_new", "faiss_GpuIndexIVFPQ_new",
+                 "faiss_StandardGpuResources_new", "faiss_IndexShards_add_shard", "b200_topk_merge"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import faiss_b200 as fb
+
+    missing = [s for s in _declared_symbols() if not hasattr(fb.lib, s)]
+    assert not missing, "declared but not exported: %s" % missing
+    assert b"sm_100a" in fb.lib.faiss_b200_version()
+
+
+def test_error_convention_without_gpu():
+    """null handles -> FAISS_EXCEPT (-2) + message, as c_api/macros_impl.h:22-36"""
+    import faiss_b200 as fb
+
+    rc = fb.lib.faiss_Index_search(None, ctypes.c_int64(1), None, ctypes.c_int64(1), None, None)
+    assert rc == -2
+    assert b"null index handle" in fb.lib.faiss_get_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """the product path must never route through oracle/"""
+    for root, _, files in os.walk(os.path.join(ROOT, "faiss_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle_np" not in txt and "libfaiss_ref" not in txt and "import oracle" not in txt, f
+
+
+def test_host_rand_perm_matches_reference(golden):
+    import faiss_b200 as fb
+
+    perm = np.empty(1000, dtype=np.int32)
+    assert fb.lib.faiss_b200_rand_perm(perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.c_size_t(1000), ctypes.c_int64(42)) == 0
+    assert np.array_equal(perm, golden["rand_perm_1000_s42"])
+
+
+def test_host_merge_matches_reference(golden):
+    from faiss_b200.distributed import merge_host
+
+    D, I = merge_host(golden["merge_allD"], golden["merge_allI"], 5, 1)
+    assert np.array_equal(I, golden["merge_I"])
+    assert np.array_equal(D, golden["merge_D"])
+
+
+def test_host_split_clusters_matches_oracle():
+    import faiss_b200 as fb
+    from oracle import oracle_np as o
+
+    rs = np.random.RandomState(3)
+    k, d, n = 12, 6, 500
+    h = rs.randint(1, 60, size=k).astype(np.float32)
+    h[[2, 7, 8]] = 0
+    c = rs.rand(k, d).astype(np.float32)
+    h2, c2 = h.copy(), c.copy()
+    ns = ctypes.c_int()
+    fp = ctypes.POINTER(ctypes.c_float)
+    assert fb.lib.faiss_b200_split_clusters(ctypes.c_size_t(d), ctypes.c_size_t(k), ctypes.c_size_t(n), h.ctypes.data_as(fp), c.ctypes.data_as(fp), ctypes.byref(ns)) == 0
+    ns2 = o.split_clusters(d, k, n, h2, c2)
+    assert ns.value == ns2 == 3
+    assert np.array_equal(h, h2)
+    assert np.allclose(c, c2, rtol=1e-6)
+
+
+def test_shard_bounds_contiguous():
+    from faiss_b200.distributed import shard_bounds
+
+    n, w = 1003, 8
+    b = [shard_bounds(n, r, w) for r in range(w)]
+    assert b[0][0] == 0 and b[-1][1] == n
+    assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))

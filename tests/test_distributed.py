@@ -1,0 +1,58 @@
+"""world_size-2 gloo test of the sharded search host logic (IndexShards semantics): contiguous
+split, successive-id translation, one all-gather, merge == unsharded result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from faiss_b200.distributed import ShardedSearcher, shard_bounds
+    from oracle import oracle_np as o
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rs = np.random.RandomState(0)
+    N, d, nq, k = 1501, 16, 23, 7
+    xb = np.floor(rs.rand(N, d) * 8).astype(np.float32)  # integer regime: exact, with ties
+    xq = np.floor(rs.rand(nq, d) * 8).astype(np.float32)
+    i0, i1 = shard_bounds(N, rank, world)
+
+    def local_search(x, kk):
+        D, I = o.knn_flat(x.numpy(), xb[i0:i1], kk, 1)  # stands in for the rank's GPU sub-index
+        return D, I
+
+    s = ShardedSearcher(local_search, i1 - i0, 1)
+    D, I = s.search(torch.from_numpy(xq), k)
+    rD, rI = o.knn_flat(xq, xb, k, 1)
+    ok = bool(np.array_equal(I.numpy(), rI) and np.array_equal(D.numpy(), rD) and s.ntotal == N)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_search_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
