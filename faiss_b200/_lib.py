@@ -23,6 +23,10 @@ if not os.path.exists(LIB_PATH):
 lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
 
 lib.faiss_get_last_error.restype = ctypes.c_char_p
+lib.faiss_b200_launch_count.restype = ctypes.c_longlong
+lib.faiss_b200_kernel_timing.restype = None
+lib.faiss_b200_kernel_timing.argtypes = [ctypes.c_int]
+lib.faiss_b200_kernel_timing_collect.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
 lib.faiss_b200_version.restype = ctypes.c_char_p
 lib.faiss_Index_ntotal.restype = ctypes.c_int64
 lib.faiss_Index_ntotal.argtypes = [ctypes.c_void_p]

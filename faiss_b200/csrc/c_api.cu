@@ -557,6 +557,20 @@ int faiss_b200_kmeans(
     CATCH_AND_HANDLE
 }
 
+// ---------------------------------------------------------------- instrumentation
+long long faiss_b200_launch_count(void) {
+    return fb200::kernelLaunchCounter();
+}
+void faiss_b200_kernel_timing(int enable) {
+    fb200::KernelTiming::enable(enable != 0);
+}
+int faiss_b200_kernel_timing_collect(const char* name, double* ms, int* launches) {
+    try {
+        fb200::KernelTiming::collect(name, ms, launches);
+    }
+    CATCH_AND_HANDLE
+}
+
 // ---------------------------------------------------------------- host utilities
 int faiss_b200_rand_perm(int* perm, size_t n, int64_t seed) {
     try {

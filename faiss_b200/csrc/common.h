@@ -79,7 +79,25 @@ class FaissException : public std::exception {
         }                                                                           \
     } while (0)
 
-#define CUDA_CHECK_LAST() CUDA_VERIFY(cudaGetLastError())
+// every kernel launch site is followed by CUDA_CHECK_LAST(): it also feeds the launch counter that
+// bench.py reports as "gpu_launches"
+long long& kernelLaunchCounter();
+#define CUDA_CHECK_LAST()                        \
+    do {                                         \
+        ::fb200::kernelLaunchCounter()++;        \
+        CUDA_VERIFY(cudaGetLastError());         \
+    } while (0)
+
+// optional per-kernel device timing (CUDA events on the launching stream), used by bench.py for
+// the roofline line; off by default
+struct KernelTiming {
+    static void enable(bool on);
+    static bool enabled();
+    static void begin(const char* name, cudaStream_t stream);
+    static void end(const char* name, cudaStream_t stream);
+    // synchronises, sums and clears: total milliseconds and number of launches for `name`
+    static void collect(const char* name, double* ms, int* launches);
+};
 
 #ifdef __CUDACC__
 #define FB_HD __host__ __device__

@@ -638,7 +638,9 @@ template <bool DUMP>
 void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
     auto kern = flat_tc_kernel<DUMP>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelTiming::begin("flat_tc", stream);
     kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
+    KernelTiming::end("flat_tc", stream);
     CUDA_CHECK_LAST();
 }
 

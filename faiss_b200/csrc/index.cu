@@ -711,7 +711,13 @@ void IvfLists::relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream
     r.size = std::max<int64_t>(total, 16) * codeSize_;
     uint8_t* nc = (uint8_t*)res_->allocMemory(r);
     r.size = std::max<int64_t>(total, 16) * sizeof(idx_t);
-    idx_t* ni = (idx_t*)res_->allocMemory(r);
+    idx_t* ni = nullptr;
+    try {
+        ni = (idx_t*)res_->allocMemory(r);
+    } catch (...) {
+        res_->deallocMemory(device_, nc);
+        throw;
+    }
     if (codes_) {
         auto ds = res_->temp(device_, sizeof(int64_t) * nlist_);
         CUDA_VERIFY(cudaMemcpyAsync(ds.data, newStart.data(), sizeof(int64_t) * nlist_, cudaMemcpyHostToDevice, stream));

@@ -377,3 +377,78 @@ std::map<int, std::map<std::string, std::pair<int, size_t>>> StandardGpuResource
 }
 
 } // namespace fb200
+
+// ---------------------------------------------------------------- launch counter / kernel timing
+#include <atomic>
+#include <cstring>
+
+namespace fb200 {
+
+long long& kernelLaunchCounter() {
+    static long long c = 0;
+    return c;
+}
+
+namespace {
+struct TimedLaunch {
+    std::string name;
+    cudaEvent_t a, b;
+};
+std::mutex g_tmu;
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+cudaEvent_t g_pendingStart = nullptr;
+} // namespace
+
+void KernelTiming::enable(bool on) {
+    std::lock_guard<std::mutex> g(g_tmu);
+    g_timing = on;
+}
+bool KernelTiming::enabled() {
+    return g_timing;
+}
+void KernelTiming::begin(const char*, cudaStream_t stream) {
+    if (!g_timing)
+        return;
+    std::lock_guard<std::mutex> g(g_tmu);
+    cudaEventCreate(&g_pendingStart);
+    cudaEventRecord(g_pendingStart, stream);
+}
+void KernelTiming::end(const char* name, cudaStream_t stream) {
+    if (!g_timing || !g_pendingStart)
+        return;
+    std::lock_guard<std::mutex> g(g_tmu);
+    TimedLaunch t;
+    t.name = name;
+    t.a = g_pendingStart;
+    cudaEventCreate(&t.b);
+    cudaEventRecord(t.b, stream);
+    g_pendingStart = nullptr;
+    g_timed.push_back(t);
+}
+void KernelTiming::collect(const char* name, double* ms, int* launches) {
+    std::lock_guard<std::mutex> g(g_tmu);
+    double tot = 0;
+    int n = 0;
+    std::vector<TimedLaunch> keep;
+    for (auto& t : g_timed) {
+        if (t.name == name) {
+            cudaEventSynchronize(t.b);
+            float e = 0;
+            cudaEventElapsedTime(&e, t.a, t.b);
+            tot += e;
+            n++;
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        } else {
+            keep.push_back(t);
+        }
+    }
+    g_timed.swap(keep);
+    if (ms)
+        *ms = tot;
+    if (launches)
+        *launches = n;
+}
+
+} // namespace fb200

@@ -147,6 +147,12 @@ FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int
    Lloyd k-means with the training set resident on the device; x host or device. */
 FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, float* centroids_out /* host [k*d] */, float* obj_out /* host [niter] or NULL */);
 
+/* ---- instrumentation (bench.py): kernels launched by this library so far; optional CUDA-event
+   timing of a named kernel ("flat_tc") on its launching stream ---- */
+FB200_API long long faiss_b200_launch_count(void);
+FB200_API void faiss_b200_kernel_timing(int enable);
+FB200_API int faiss_b200_kernel_timing_collect(const char* name, double* ms_out, int* launches_out);
+
 /* ---- host-side utilities of the path (no GPU needed) ----
    rand_perm: faiss/utils/random.cpp:188-199; split_clusters: faiss/impl/ClusteringHelpers.cpp:177-240;
    merge_knn_results: faiss/utils/Heap.cpp:166-238 (all_* laid out [nshard][n][k]) */

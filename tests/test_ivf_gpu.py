@@ -1,0 +1,212 @@
+"""GPU parity tests for IVF-Flat / IVF-PQ, k-means and IndexShards, through the C ABI.
+
+Model: faiss/gpu/test/TestGpuIndexIVFPQ.cpp:183-897, TestGpuIndexIVFFlat.cpp, test_gpu_index.py:124-196
+(search == search_preassigned bit-exact), test_gpu_basics.py:117-133 (k-means objective),
+test_multi_gpu.py:23-43 (sharded flat == unsharded)."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _lists_from_golden(golden, name, M):
+    lens = golden["ivfpq_%s_lens" % name]
+    codes_all, ids_all = golden["ivfpq_%s_codes" % name], golden["ivfpq_%s_ids" % name]
+    codes, ids = [], []
+    c0 = i0 = 0
+    for n in lens:
+        codes.append(codes_all[c0 : c0 + n * M])
+        ids.append(ids_all[i0 : i0 + n])
+        c0 += n * M
+        i0 += n
+    return codes, ids
+
+
+@pytest.mark.parametrize("metric,name", [(1, "l2"), (0, "ip")])
+def test_ivfpq_copyfrom_golden_search(res, golden, metric, name):
+    """clone the reference-trained CPU index (centroids, PQ, ArrayInvertedLists bytes) and search:
+    TestGpuIndexIVFPQ.cpp CopyFrom + Query, tolerance eps=1e-4 rel (reference test uses 0.035)"""
+    import faiss_b200 as fb
+
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    xq = o.float_rand(nq * d, 22).reshape(nq, d)
+    codes, ids = _lists_from_golden(golden, name, M)
+    idx = fb.GpuIndexIVFPQ(res, d, nlist, M, 8, metric)
+    idx.setCoarseCentroids(golden["ivfpq_%s_centroids" % name])
+    idx.setPQCentroids(golden["ivfpq_%s_pq" % name])
+    for l in range(nlist):
+        idx.setList(l, codes[l], ids[l])
+    idx.setIsTrained(True)
+    assert idx.ntotal == N
+    idx.nprobe = nprobe
+    D, I = idx.search(xq, k)
+    o.compare_lists(golden["ivfpq_%s_D" % name], golden["ivfpq_%s_I" % name], D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+    # copyTo: byte-exact inverted lists (testIVFEquality, faiss/gpu/test/TestUtils.h:95-127)
+    for l in range(nlist):
+        assert np.array_equal(idx.getListVectorData(l), codes[l])
+        assert np.array_equal(idx.getListIndices(l), ids[l])
+
+
+def test_ivfpq_add_reproduces_reference_lists(res, golden):
+    """device-side assign -> residual -> PQ encode -> append gives the reference's lists"""
+    import faiss_b200 as fb
+
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    xb = o.float_rand(N * d, 21).reshape(N, d)
+    codes, ids = _lists_from_golden(golden, "l2", M)
+    idx = fb.GpuIndexIVFPQ(res, d, nlist, M, 8, 1)
+    idx.setCoarseCentroids(golden["ivfpq_l2_centroids"])
+    idx.setPQCentroids(golden["ivfpq_l2_pq"])
+    idx.setIsTrained(True)
+    idx.add(xb[:2500])
+    idx.add(xb[2500:])  # two batches: append order must stay insertion order
+    assert idx.ntotal == N
+    bad = 0
+    for l in range(nlist):
+        gi = idx.getListIndices(l)
+        gc = idx.getListVectorData(l).reshape(-1, M)
+        if gi.size == ids[l].size and np.array_equal(gi, ids[l]):
+            bad += int((gc != codes[l].reshape(-1, M)).any(axis=1).sum())
+        else:  # an assignment flipped on an fp near-tie
+            bad += len(set(gi.tolist()) ^ set(ids[l].tolist()))
+    assert bad <= N * 0.002
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+def test_ivfflat_vs_oracle_and_preassigned(res, metric):
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(3)
+    N, d, nlist, nq, k = 20000, 40, 50, 60, 20
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    idx = fb.GpuIndexIVFFlat(res, d, nlist, metric)
+    assert not idx.is_trained
+    with pytest.raises(fb.FaissError):
+        idx.add(xb[:10])  # "Index not trained"
+    idx.train(xb)
+    ids = (np.arange(N, dtype=np.int64) * 7 + 3)
+    idx.add_with_ids(xb, ids)
+    idx.nprobe = 9
+    D, I = idx.search(xq, k)
+    cent = idx.getCoarseCentroids()
+    lv = [idx.getListVectorData(l).view(np.float32) for l in range(nlist)]
+    li = [idx.getListIndices(l) for l in range(nlist)]
+    assert sum(x.size for x in li) == N
+    rD, rI = o.ivfflat_search(xq, k, 9, cent, lv, li, metric)
+    o.compare_lists(rD, rI, D, I, eps=1e-4, pct_max_diff1=0.01, pct_max_diffN=0.005)
+    # search == search_preassigned, bit-exact (faiss/gpu/test/test_gpu_index.py:190-194)
+    cD, cI = o.knn_flat(xq, cent, 9, metric)
+    D2, I2 = idx.search_preassigned(xq, k, cI, cD)
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)
+    # nprobe limit
+    idx.nprobe = 4096
+    with pytest.raises(fb.FaissError):
+        idx.search(xq, k)
+
+
+@pytest.mark.parametrize("M", [4, 16, 32])
+def test_ivfpq_train_add_search_vs_oracle(res, M):
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(M)
+    N, d, nlist, nq, k = 30000, 64, 40, 50, 100
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    idx = fb.GpuIndexIVFPQ(res, d, nlist, M, 8, 1)
+    idx.setClustering(niter=5)
+    idx.setPQClustering(niter=6)
+    idx.train(xb)
+    idx.add(xb)
+    idx.nprobe = 6
+    D, I = idx.search(xq, k)
+    lc = [idx.getListVectorData(l) for l in range(nlist)]
+    li = [idx.getListIndices(l) for l in range(nlist)]
+    rD, rI = o.ivfpq_search(xq, k, 6, idx.getCoarseCentroids(), idx.getPQCentroids(), lc, li, 1)
+    o.compare_lists(rD, rI, D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+    # recall sanity vs exact ground truth (tests/test_ivfpq_indexing.cpp:17-97 style)
+    gt = o.knn_flat(xq, xb, 1, 1)[1]
+    assert o.recall_at(I, gt, 100) > 0.3
+    # reserve / reclaim keep contents
+    before = [idx.getListIndices(l).copy() for l in range(0, nlist, 7)]
+    idx.reserveMemory(2 * N)
+    idx.reclaimMemory()
+    after = [idx.getListIndices(l) for l in range(0, nlist, 7)]
+    assert all(np.array_equal(a, b) for a, b in zip(before, after))
+    D3, I3 = idx.search(xq, k)
+    assert np.array_equal(I, I3)
+
+
+def test_ivfpq_constraints(res):
+    import faiss_b200 as fb
+
+    with pytest.raises(fb.FaissError):
+        fb.GpuIndexIVFPQ(res, 64, 16, 8, 4)  # nbits != 8 (faiss/gpu/GpuIndexIVFPQ.cu:124-131)
+    with pytest.raises(fb.FaissError):
+        fb.GpuIndexIVFPQ(res, 30, 16, 8, 8)  # d % M != 0
+
+
+def test_kmeans_matches_reference(res, golden):
+    """same seeds -> same sampling and init as faiss::Clustering; objective and centroids agree
+    (test_gpu_basics.py:117-133 uses np.allclose on the objective)"""
+    import faiss_b200 as fb
+
+    x = o.float_rand(5000 * 8, 31).reshape(5000, 8)
+    cent, obj = fb.kmeans(res, x, 20, niter=8, seed=123)
+    assert np.allclose(obj, golden["kmeans_obj"], rtol=1e-4)
+    assert np.allclose(cent, golden["kmeans_centroids"], rtol=1e-3, atol=1e-4)
+    cent, obj = fb.kmeans(res, x, 4, niter=5, seed=99, max_points_per_centroid=256)  # subsampled run
+    assert np.allclose(obj, golden["kmeans_sub_obj"], rtol=1e-4)
+    assert np.allclose(cent, golden["kmeans_sub_centroids"], rtol=1e-3, atol=1e-4)
+
+
+def test_kmeans_large_codebook_path(res):
+    """k*d > shared memory -> global RED path; compare with the oracle"""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(5)
+    x = rs.rand(30000, 64).astype(np.float32)
+    cent, obj = fb.kmeans(res, x, 512, niter=4, seed=7)
+    co, oo = o.kmeans(x, 512, niter=4, seed=7)
+    assert np.allclose(obj, oo, rtol=1e-4)
+    assert np.allclose(cent, co, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("threaded", [False, True])
+def test_index_shards_flat_equals_unsharded(res, threaded):
+    """faiss/gpu/test/test_multi_gpu.py:23-43: sharded flat == reference ids (np.all(I == I_ref))"""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(1)
+    d = 32
+    xb = rs.rand(1000, d).astype(np.float32)
+    xq = rs.rand(50, d).astype(np.float32)
+    sh = fb.IndexShards(d, threaded=threaded, successive_ids=True)
+    subs = [fb.GpuIndexFlatL2(res, d) for _ in range(3)]
+    for s in subs:
+        sh.add_shard(s)
+    sh.add(xb)
+    assert sh.ntotal == 1000 and [s.ntotal for s in subs] == [333, 333, 334]
+    D, I = sh.search(xq, 10)
+    rD, rI = o.knn_flat(xq, xb, 10, 1)
+    assert np.array_equal(I, rI)
+    one = fb.GpuIndexFlatL2(res, d)
+    one.add(xb)
+    D1, I1 = one.search(xq, 10)
+    assert np.array_equal(I, I1) and np.array_equal(D, D1)
+    with pytest.raises(fb.FaissError):
+        sh.add_with_ids(xb[:3], np.arange(3))  # successive_ids + explicit ids (IndexShards.cpp:143-150)
+
+
+def test_device_merge_kernel_vs_reference_merge(res, golden):
+    import torch
+
+    import faiss_b200 as fb
+
+    allD = torch.from_numpy(golden["merge_allD"]).cuda().permute(1, 0, 2).contiguous()
+    allI = torch.from_numpy(golden["merge_allI"]).cuda().permute(1, 0, 2).contiguous()
+    D, I = fb.topk_merge(res, allD, allI, 5, 1)
+    assert np.array_equal(I.cpu().numpy(), golden["merge_I"])
+    assert np.array_equal(D.cpu().numpy(), golden["merge_D"])
