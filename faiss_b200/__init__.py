@@ -77,7 +77,7 @@ class StandardGpuResources:
         check(lib.faiss_StandardGpuResources_new(ctypes.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.faiss_StandardGpuResources_free(self._h)
             self._h = None
 
@@ -124,9 +124,26 @@ class Index:
         self._keep = []
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.faiss_Index_free(self._h)
             self._h = None
+
+    def _use_torch_stream(self, *tensors):
+        """PyTorch interop as in faiss.contrib.torch_utils: when an argument is a CUDA tensor, order
+        the library's work on torch's current stream (StandardGpuResources::setDefaultStream,
+        faiss/gpu/StandardGpuResources.h:75,232) so that torch ops before/after the call are
+        correctly ordered with it."""
+        for t in tensors:
+            if t is not None and _is_torch(t) and t.is_cuda:
+                import torch
+
+                dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+                for r in self._resources():
+                    r.setDefaultStream(dev, torch.cuda.current_stream(dev).cuda_stream)
+                return
+
+    def _resources(self):
+        return [r for r in self._keep if isinstance(r, StandardGpuResources)]
 
     # -- fields
     @property
@@ -161,16 +178,19 @@ class Index:
 
     def train(self, x):
         x = self._check_x(x)
+        self._use_torch_stream(x)
         check(lib.faiss_Index_train(self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f)))
 
     def add(self, x):
         x = self._check_x(x)
+        self._use_torch_stream(x)
         check(lib.faiss_Index_add(self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f)))
 
     def add_with_ids(self, x, ids):
         x = self._check_x(x)
         ids = _as_i64(ids)
         assert ids.shape == (x.shape[0],)
+        self._use_torch_stream(x, ids)
         check(lib.faiss_Index_add_with_ids(self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f), _ptr(ids, _c_i64)))
 
     def search(self, x, k, D=None, I=None):
@@ -180,6 +200,7 @@ class Index:
             D = _empty_like_residency(x, (n, k), np.float32)
         if I is None:
             I = _empty_like_residency(x, (n, k), np.int64)
+        self._use_torch_stream(x, D, I)
         check(
             lib.faiss_Index_search(
                 self._h, ctypes.c_int64(n), _ptr(x, _c_f), ctypes.c_int64(k), _ptr(D, _c_f), _ptr(I, _c_i64)
@@ -191,6 +212,7 @@ class Index:
         x = self._check_x(x)
         n = x.shape[0]
         I = _empty_like_residency(x, (n, k), np.int64)
+        self._use_torch_stream(x)
         check(lib.faiss_Index_assign(self._h, ctypes.c_int64(n), _ptr(x, _c_f), _ptr(I, _c_i64), ctypes.c_int64(k)))
         return I
 
@@ -223,6 +245,7 @@ class Index:
         x = self._check_x(x)
         keys = _as_i64(keys)
         out = _empty_like_residency(x, tuple(x.shape), np.float32)
+        self._use_torch_stream(x, keys)
         check(
             lib.faiss_Index_compute_residual_n(
                 self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f), _ptr(out, _c_f), _ptr(keys, _c_i64)
@@ -351,6 +374,7 @@ class GpuIndexIVF(Index):
         centroid_dis = _as_f32(centroid_dis)
         D = _empty_like_residency(x, (n, k), np.float32)
         I = _empty_like_residency(x, (n, k), np.int64)
+        self._use_torch_stream(x, assign)
         check(
             lib.faiss_GpuIndexIVF_search_preassigned(
                 self._h,
@@ -438,6 +462,12 @@ class IndexShards(Index):
         check(lib.faiss_IndexShards_add_shard(self._h, index._h))
         self._shards.append(index)
 
+    def _resources(self):
+        out = []
+        for s in self._shards:
+            out.extend(s._resources())
+        return out
+
     def remove_shard(self, index):
         check(lib.faiss_IndexShards_remove_shard(self._h, index._h))
         self._shards.remove(index)
@@ -450,7 +480,7 @@ class IndexShards(Index):
 
     def __del__(self):
         # free the meta index before the shards it points to
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:
             lib.faiss_Index_free(self._h)
             self._h = None
         self._shards = []
@@ -485,6 +515,7 @@ def flat_search_exact(res, Y, Q, k, metric=METRIC_L2, device=0):
     import torch
 
     assert Y.is_cuda and Q.is_cuda
+    res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
     nq = Q.shape[0]
     D = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
@@ -502,6 +533,7 @@ def topk_merge(res, D_in, I_in, k, metric=METRIC_L2, id_offsets=None, device=0):
     import torch
 
     nq, nshard, kin = D_in.shape
+    res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
     D = torch.empty((nq, k), dtype=torch.float32, device=D_in.device)
     I = torch.empty((nq, k), dtype=torch.int64, device=D_in.device)
     check(
@@ -519,6 +551,7 @@ def flat_tc_scores_debug(res, Q16, Y16, device=0):
 
     nq, dpad = Q16.shape
     N = Y16.shape[0]
+    res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
     npad = (N + 127) // 128 * 128
     S = torch.zeros((nq, npad), dtype=torch.float32, device=Q16.device)
     check(

@@ -74,10 +74,15 @@ class ShardedSearcher:
             D = torch.from_numpy(D)
             I = torch.from_numpy(I)
         nq = D.shape[0]
-        allD = torch.empty((self.world, nq, k), dtype=torch.float32, device=D.device)
-        allI = torch.empty((self.world, nq, k), dtype=torch.int64, device=D.device)
-        dist.all_gather_into_tensor(allD.view(-1), D.contiguous().view(-1), group=self.group)
-        dist.all_gather_into_tensor(allI.view(-1), I.contiguous().view(-1), group=self.group)
+        # ONE all-gather: distances (fp32) and labels (int64) travel in one byte message per rank
+        nD, nI = nq * k * 4, nq * k * 8
+        send = torch.empty(nD + nI, dtype=torch.uint8, device=D.device)
+        send[:nD] = D.contiguous().view(torch.uint8).view(-1)
+        send[nD:] = I.contiguous().view(torch.uint8).view(-1)
+        recv = torch.empty((self.world, nD + nI), dtype=torch.uint8, device=D.device)
+        dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
+        allD = recv[:, :nD].contiguous().view(torch.float32).view(self.world, nq, k)
+        allI = recv[:, nD:].contiguous().view(torch.int64).view(self.world, nq, k)
         if D.is_cuda:
             if self._off_dev is None:
                 self._off_dev = torch.from_numpy(self.offsets).to(D.device)
