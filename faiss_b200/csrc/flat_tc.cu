@@ -50,6 +50,7 @@ constexpr int kKBlockBytes = kTileN * kKBlock * 2; // 16 KiB per (128 rows x 64 
 constexpr int kThreads = 320;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kMaxYStages = 6;
+constexpr int kBiasSlots = 8;     // per-tile bias (512 B) + tile id ring, producer -> epilogue
 
 struct TcParams {
     int numUnits;
@@ -94,7 +95,11 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
     uint64_t* y_empty = y_full + kMaxYStages;
     uint64_t* t_full = y_empty + kMaxYStages;
     uint64_t* t_empty = t_full + kAccStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + kAccStages);
+    uint64_t* b_full = t_empty + kAccStages;
+    uint64_t* b_empty = b_full + kBiasSlots;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kBiasSlots);
+    int* tileS = reinterpret_cast<int*>(tmem_slot + 2);                         // [kBiasSlots]
+    float* biasS = reinterpret_cast<float*>(tileS + kBiasSlots + 2);            // [kBiasSlots][128], 16B aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -112,6 +117,10 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             ptx::mbar_init(&t_full[i], 1);
             ptx::mbar_init(&t_empty[i], kEpiWarps);
         }
+        for (int i = 0; i < kBiasSlots; i++) {
+            ptx::mbar_init(&b_full[i], 1);
+            ptx::mbar_init(&b_empty[i], kEpiWarps);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -125,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int ys = 0;
-            uint32_t yphase = 0;
+            int ys = 0, bs = 0;
+            uint32_t yphase = 0, bphase = 0;
             int it = 0;
             for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
                 const int qt = u / p.slices;
@@ -144,6 +153,15 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     if (++ys == p.yStages) {
                         ys = 0;
                         yphase ^= 1;
+                    }
+                    // per-tile bias + tile id for the epilogue
+                    ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+                    tileS[bs] = t;
+                    ptx::mbar_arrive_expect_tx(&b_full[bs], kTileN * 4);
+                    ptx::bulk_load_1d(biasS + bs * kTileN, p.bias + (long long)t * kTileN, kTileN * 4, &b_full[bs]);
+                    if (++bs == kBiasSlots) {
+                        bs = 0;
+                        bphase ^= 1;
                     }
                 }
             }
@@ -198,67 +216,29 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
         const int half = ew >> 2;      // which 64 columns of the tile
         const int row = quarter * 32 + lane;
         const float inv = *p.invScalePtr;
-        int as = 0;
-        uint32_t aphase = 0;
+        int as = 0, bs = 0;
+        uint32_t aphase = 0, bphase = 0;
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
             const int qt = u / p.slices;
             const int sl = u % p.slices;
             const int q = qt * kTileM + row;
             const float thr = (!DUMP && q < p.nq) ? p.thr[q] : CUDART_INF_F;
             const long long seg = ((long long)u * kTileM + row) * 2 + half;
-            uint2* buf = p.cand + seg * p.cap;
+            uint2* buf = DUMP ? nullptr : p.cand + seg * p.cap;
             int cnt = 0;
             const int pb = p.tileBegin + sl * p.tilesPerSlice;
             const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
             for (int pp = pb; pp < pe; pp++) {
-                const int t = perm_tile(p, pp);
+                ptx::mbar_wait(&b_full[bs], bphase);
+                const int t = tileS[bs];
                 ptx::mbar_wait(&t_full[as], aphase);
                 ptx::tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 2; c++) {
-                    const int col0 = half * 64 + c * 32;
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32b_x32(
-                            tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kTileN + col0), r);
-                    float b[32];
-                    const float4* bp = reinterpret_cast<const float4*>(p.bias + (long long)t * kTileN + col0);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float4 v = __ldg(bp + j);
-                        b[4 * j + 0] = v.x;
-                        b[4 * j + 1] = v.y;
-                        b[4 * j + 2] = v.z;
-                        b[4 * j + 3] = v.w;
-                    }
-                    ptx::tmem_ld_wait();
-                    if (DUMP) {
-                        if (q < p.nq) {
-                            float* dst = p.dump + (long long)q * p.dumpLd + (long long)t * kTileN + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++)
-                                dst[j] = __uint_as_float(r[j]);
-                        }
-                    } else {
-                        float m = -CUDART_INF_F;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            b[j] = fmaf(__uint_as_float(r[j]), inv, b[j]);
-                            m = fmaxf(m, b[j]);
-                        }
-                        if (m > thr) {
-                            const unsigned rowBase = (unsigned)t * kTileN + col0;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (b[j] > thr) {
-                                    if (cnt < p.cap)
-                                        buf[cnt] = make_uint2(__float_as_uint(b[j]), rowBase + j);
-                                    cnt++;
-                                }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), r0);
+                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN + 32), r1);
+                ptx::tmem_ld_wait();
+                // the accumulator stage is in registers now: hand it back to the MMA warp early
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
@@ -266,6 +246,54 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                 if (++as == kAccStages) {
                     as = 0;
                     aphase ^= 1;
+                }
+                if (DUMP) {
+                    if (q < p.nq) {
+                        float* dst = p.dump + (long long)q * p.dumpLd + (long long)t * kTileN + half * 64;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            dst[j] = __uint_as_float(r0[j]);
+                            dst[32 + j] = __uint_as_float(r1[j]);
+                        }
+                    }
+                } else {
+                    const float4* bp = reinterpret_cast<const float4*>(biasS + bs * kTileN + half * 64);
+                    float v[64];
+                    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = bp[j];
+                        ptx::fma2(v[4 * j], v[4 * j + 1], __uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), inv, b.x, b.y);
+                        ptx::fma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]), inv, b.z, b.w);
+                        m0 = ptx::max3(m0, v[4 * j], v[4 * j + 1]);
+                        m1 = ptx::max3(m1, v[4 * j + 2], v[4 * j + 3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = bp[8 + j];
+                        ptx::fma2(v[32 + 4 * j], v[33 + 4 * j], __uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), inv, b.x, b.y);
+                        ptx::fma2(v[34 + 4 * j], v[35 + 4 * j], __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]), inv, b.z, b.w);
+                        m0 = ptx::max3(m0, v[32 + 4 * j], v[33 + 4 * j]);
+                        m1 = ptx::max3(m1, v[34 + 4 * j], v[35 + 4 * j]);
+                    }
+                    if (fmaxf(m0, m1) > thr) {
+                        const unsigned rowBase = (unsigned)t * kTileN + half * 64;
+#pragma unroll
+                        for (int j = 0; j < 64; j++) {
+                            if (v[j] > thr) {
+                                if (cnt < p.cap)
+                                    buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
+                                cnt++;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0)
+                    ptx::mbar_arrive(&b_empty[bs]);
+                if (++bs == kBiasSlots) {
+                    bs = 0;
+                    bphase ^= 1;
                 }
             }
             if (!DUMP)
@@ -628,7 +656,7 @@ struct SmemPlan {
 SmemPlan planSmem(int KB) {
     const size_t stage = (size_t)KB * kKBlockBytes;
     const size_t budget = 220 * 1024;
-    const size_t fixed = 1024 /*align slack*/ + 256 /*barriers*/ + stage /*Q*/;
+    const size_t fixed = 1024 /*align slack*/ + 512 /*barriers, tile ids*/ + kBiasSlots * kTileN * 4 /*bias ring*/ + stage /*Q*/;
     int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
     FB_THROW_IF_NOT_MSG(ys >= 2, "dimension too large for the tensor-core Flat kernel");
     return {ys, fixed + ys * stage};

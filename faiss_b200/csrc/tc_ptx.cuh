@@ -87,6 +87,32 @@ __device__ __forceinline__ void tma_load_3d(
             : "memory");
 }
 
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (bytes multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(smem_u32(smem_dst)),
+            "l"(reinterpret_cast<uint64_t>(gsrc)),
+            "r"(bytes),
+            "r"(smem_u32(bar))
+            : "memory");
+}
+
+// ------------------------------------------------------------------ packed fp32 math (sm_100)
+// (o0,o1) = (a0,a1) * (s,s) + (c0,c1)   -> one FFMA2
+__device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float s, float c0, float c1) {
+    asm("{\n.reg .b64 ra, rs, rc, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rs, {%4,%4};\nmov.b64 rc, {%5,%6};\n"
+        "fma.rn.f32x2 rd, ra, rs, rc;\nmov.b64 {%0,%1}, rd;\n}"
+        : "=f"(o0), "=f"(o1)
+        : "f"(a0), "f"(a1), "f"(s), "f"(c0), "f"(c1));
+}
+// 3-input max -> one FMNMX3
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
