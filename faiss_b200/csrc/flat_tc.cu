@@ -55,6 +55,7 @@ constexpr int kBiasSlots = 8;     // per-tile bias (512 B) + tile id ring, produ
 struct TcParams {
     int numUnits;
     int slices;
+    int qTiles;         // unit u = slice * qTiles + queryTile: neighbouring CTAs stream the SAME database tiles (L2 reuse)
     int tileBegin;      // permuted position range of this round
     int tileEnd;
     int tilesPerSlice;
@@ -74,6 +75,52 @@ struct TcParams {
 
 __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
     return (int)(((unsigned long long)pos * p.permA + p.permB) % p.numTiles);
+}
+
+// Filter 32 columns of this thread's query row: score = acc * inv + bias, chunk maximum against the
+// query's threshold; the rare survivors are appended to the thread-private candidate segment.
+// FFMA2 + FMNMX3: one instruction per element.
+template <bool DUMP>
+__device__ __forceinline__ void epi_filter32(
+        const TcParams& p,
+        const uint32_t (&r)[32],
+        int q,
+        long long colBase, // global row index of column 0 of this chunk
+        float inv,
+        float thr,
+        uint32_t bp, // shared address of the 32 biases
+        uint2* buf,
+        int& cnt) {
+    if (DUMP) {
+        if (q < p.nq) {
+            float* dst = p.dump + (long long)q * p.dumpLd + colBase;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                dst[j] = __uint_as_float(r[j]);
+        }
+        return;
+    }
+    float v[32];
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 b = ptx::lds128(bp + j * 16);
+        ptx::fma2(v[4 * j], v[4 * j + 1], __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), inv, b.x, b.y);
+        ptx::fma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), inv, b.z, b.w);
+        m0 = ptx::max3(m0, v[4 * j], v[4 * j + 1]);
+        m1 = ptx::max3(m1, v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (fmaxf(m0, m1) > thr) {
+        const unsigned rowBase = (unsigned)colBase;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (v[j] > thr) {
+                if (cnt < p.cap)
+                    buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
+                cnt++;
+            }
+        }
+    }
 }
 
 template <bool DUMP>
@@ -138,8 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             uint32_t yphase = 0, bphase = 0;
             int it = 0;
             for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
-                const int qt = u / p.slices;
-                const int sl = u % p.slices;
+                const int qt = u % p.qTiles;
+                const int sl = u / p.qTiles;
                 ptx::mbar_wait(q_empty, (it & 1) ^ 1);
                 ptx::mbar_arrive_expect_tx(q_full, (uint32_t)stageBytes);
                 ptx::tma_load_3d(sQ, &mapQ, q_full, 0, qt * kTileM, 0);
@@ -156,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     }
                     // per-tile bias + tile id for the epilogue
                     ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-                    tileS[bs] = t;
+                    ptx::sts32(ptx::smem_u32(tileS + bs), t);
                     ptx::mbar_arrive_expect_tx(&b_full[bs], kTileN * 4);
                     ptx::bulk_load_1d(biasS + bs * kTileN, p.bias + (long long)t * kTileN, kTileN * 4, &b_full[bs]);
                     if (++bs == kBiasSlots) {
@@ -176,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             const uint32_t sQaddr = ptx::smem_u32(sQ);
             const uint32_t sYaddr = ptx::smem_u32(sY);
             for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
-                const int sl = u % p.slices;
+                const int sl = u / p.qTiles;
                 const int pb = p.tileBegin + sl * p.tilesPerSlice;
                 const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
                 ptx::mbar_wait(q_full, it & 1);
@@ -220,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
         uint32_t aphase = 0, bphase = 0;
         const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
-            const int qt = u / p.slices;
-            const int sl = u % p.slices;
+            const int qt = u % p.qTiles;
+            const int sl = u / p.qTiles;
             const int q = qt * kTileM + row;
             const float thr = (!DUMP && q < p.nq) ? p.thr[q] : CUDART_INF_F;
             const long long seg = ((long long)u * kTileM + row) * 2 + half;
@@ -229,16 +276,21 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             int cnt = 0;
             const int pb = p.tileBegin + sl * p.tilesPerSlice;
             const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
+            // Software pipeline at 32-column granularity: while chunk A (columns 0..31 of this warp's
+            // half) is filtered, the TMEM load of chunk B is in flight, and vice versa across tiles.
+            uint32_t ra[32], rb[32];
+            ptx::mbar_wait(&t_full[as], aphase);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), ra);
             for (int pp = pb; pp < pe; pp++) {
                 ptx::mbar_wait(&b_full[bs], bphase);
-                const int t = tileS[bs];
-                ptx::mbar_wait(&t_full[as], aphase);
-                ptx::tc_fence_after();
-                uint32_t r0[32], r1[32];
-                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), r0);
-                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN + 32), r1);
-                ptx::tmem_ld_wait();
-                // the accumulator stage is in registers now: hand it back to the MMA warp early
+                const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
+                const long long colBase = (long long)t * kTileN + half * 64;
+                const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * 64);
+                ptx::tmem_ld_wait(); // A landed
+                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN + 32), rb);
+                epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
+                ptx::tmem_ld_wait(); // B landed: the accumulator stage can go back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
@@ -247,47 +299,12 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     as = 0;
                     aphase ^= 1;
                 }
-                if (DUMP) {
-                    if (q < p.nq) {
-                        float* dst = p.dump + (long long)q * p.dumpLd + (long long)t * kTileN + half * 64;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            dst[j] = __uint_as_float(r0[j]);
-                            dst[32 + j] = __uint_as_float(r1[j]);
-                        }
-                    }
-                } else {
-                    const float4* bp = reinterpret_cast<const float4*>(biasS + bs * kTileN + half * 64);
-                    float v[64];
-                    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b = bp[j];
-                        ptx::fma2(v[4 * j], v[4 * j + 1], __uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), inv, b.x, b.y);
-                        ptx::fma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]), inv, b.z, b.w);
-                        m0 = ptx::max3(m0, v[4 * j], v[4 * j + 1]);
-                        m1 = ptx::max3(m1, v[4 * j + 2], v[4 * j + 3]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b = bp[8 + j];
-                        ptx::fma2(v[32 + 4 * j], v[33 + 4 * j], __uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), inv, b.x, b.y);
-                        ptx::fma2(v[34 + 4 * j], v[35 + 4 * j], __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]), inv, b.z, b.w);
-                        m0 = ptx::max3(m0, v[32 + 4 * j], v[33 + 4 * j]);
-                        m1 = ptx::max3(m1, v[34 + 4 * j], v[35 + 4 * j]);
-                    }
-                    if (fmaxf(m0, m1) > thr) {
-                        const unsigned rowBase = (unsigned)t * kTileN + half * 64;
-#pragma unroll
-                        for (int j = 0; j < 64; j++) {
-                            if (v[j] > thr) {
-                                if (cnt < p.cap)
-                                    buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
-                                cnt++;
-                            }
-                        }
-                    }
+                if (pp + 1 < pe) {
+                    ptx::mbar_wait(&t_full[as], aphase);
+                    ptx::tc_fence_after();
+                    ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), ra);
                 }
+                epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
                 __syncwarp();
                 if (lane == 0)
                     ptx::mbar_arrive(&b_empty[bs]);
@@ -442,7 +459,7 @@ __global__ void tc_select_kernel(
     int overflow = 0;
     const int qt = q / kTileM, row = q % kTileM;
     for (int s = 0; s < slices; s++) {
-        const int u = qt * slices + s;
+        const int u = s * ((nq + kTileM - 1) / kTileM) + qt;
         for (int h = 0; h < 2; h++) {
             const long long seg = ((long long)u * kTileM + row) * 2 + h;
             int c = candCount[seg];
@@ -738,6 +755,7 @@ void runFlatTcScoresDebug(
     CUDA_VERIFY(cudaMemcpyAsync(one, &h1, sizeof(float), cudaMemcpyHostToDevice, stream));
     TcParams p{};
     p.slices = 1;
+    p.qTiles = (int)qTiles;
     p.numUnits = (int)qTiles;
     p.tileBegin = 0;
     p.tileEnd = (int)numTiles;
@@ -894,6 +912,7 @@ void runFlatTcSearch(
         for (auto& r : rounds) {
             TcParams p{};
             p.slices = r.slices;
+            p.qTiles = (int)qTiles;
             p.numUnits = (int)(qTiles * r.slices);
             p.tileBegin = r.begin;
             p.tileEnd = r.end;

@@ -123,13 +123,14 @@ __global__ void copy_lists_kernel(
         const int* len,
         const int64_t* dstStart,
         int codeSize,
+        int group, // codes are copied in whole groups (32 for the interleaved PQ layout)
         uint8_t* dstCodes,
         idx_t* dstIds) {
     const int l = blockIdx.x;
     const int64_t n = len[l];
     const uint8_t* s = srcCodes + srcStart[l] * codeSize;
     uint8_t* t = dstCodes + dstStart[l] * codeSize;
-    const int64_t bytes = n * codeSize;
+    const int64_t bytes = ((n + group - 1) / group) * group * codeSize;
     if ((codeSize & 15) == 0) {
         for (int64_t i = threadIdx.x; i < (bytes >> 4); i += blockDim.x)
             reinterpret_cast<uint4*>(t)[i] = reinterpret_cast<const uint4*>(s)[i];
@@ -641,8 +642,15 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
 // ------------------------------------------------------------------------------------------
 // IvfLists
 // ------------------------------------------------------------------------------------------
-IvfLists::IvfLists(GpuResources* res, int device, int64_t nlist, int codeSize)
-        : res_(res), device_(device), nlist_(nlist), codeSize_(codeSize), hStart_(nlist, 0), hCap_(nlist, 0), hLen_(nlist, 0) {
+IvfLists::IvfLists(GpuResources* res, int device, int64_t nlist, int codeSize, bool pqInterleaved)
+        : res_(res),
+          device_(device),
+          nlist_(nlist),
+          codeSize_(codeSize),
+          interleaved_(pqInterleaved),
+          hStart_(nlist, 0),
+          hCap_(nlist, 0),
+          hLen_(nlist, 0) {
     AllocRequest r;
     r.type = AllocType::IVFLists;
     r.device = device;
@@ -694,14 +702,14 @@ int IvfLists::maxListLength() const {
     return m;
 }
 
-// move every list to a new arena with the given capacities (multiples of 16 elements so that any
-// code size keeps 16-byte aligned list starts)
+// move every list to a new arena with the given capacities (multiples of 32 elements: 16-byte
+// aligned list starts for any code size, whole groups for the interleaved PQ layout)
 void IvfLists::relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream) {
     std::vector<int64_t> newStart(nlist_);
     int64_t total = 0;
     for (int64_t l = 0; l < nlist_; l++) {
         newStart[l] = total;
-        total += round_up(newCap[l], 16);
+        total += round_up(newCap[l], 32);
     }
     AllocRequest r;
     r.type = AllocType::IVFLists;
@@ -710,6 +718,8 @@ void IvfLists::relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream
     r.stream = stream;
     r.size = std::max<int64_t>(total, 16) * codeSize_;
     uint8_t* nc = (uint8_t*)res_->allocMemory(r);
+    if (interleaved_) // tail lanes of the last group are read (and masked) by the scan: keep them defined
+        CUDA_VERIFY(cudaMemsetAsync(nc, 0, r.size, stream));
     r.size = std::max<int64_t>(total, 16) * sizeof(idx_t);
     idx_t* ni = nullptr;
     try {
@@ -722,7 +732,7 @@ void IvfLists::relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream
         auto ds = res_->temp(device_, sizeof(int64_t) * nlist_);
         CUDA_VERIFY(cudaMemcpyAsync(ds.data, newStart.data(), sizeof(int64_t) * nlist_, cudaMemcpyHostToDevice, stream));
         copy_lists_kernel<<<(unsigned)nlist_, 256, 0, stream>>>(
-                codes_, ids_, dStart_, dLen_, ds.as<int64_t>(), codeSize_, nc, ni);
+                codes_, ids_, dStart_, dLen_, ds.as<int64_t>(), codeSize_, interleaved_ ? 32 : 1, nc, ni);
         CUDA_CHECK_LAST();
         CUDA_VERIFY(cudaStreamSynchronize(stream));
         res_->deallocMemory(device_, codes_);
@@ -733,7 +743,7 @@ void IvfLists::relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream
     arenaElems_ = total;
     hStart_ = newStart;
     for (int64_t l = 0; l < nlist_; l++)
-        hCap_[l] = round_up(newCap[l], 16);
+        hCap_[l] = round_up(newCap[l], 32);
     uploadMeta_(stream);
 }
 
@@ -787,7 +797,10 @@ idx_t IvfLists::append(idx_t n, const uint8_t* rowsDev, const idx_t* idsDev, con
         relayout_(cap, stream);
     auto offsets = res_->temp(device_, sizeof(int) * n);
     runIvfAppendOffsets(assignDev, n, nlist_, dLen_, offsets.as<int>(), nullptr, stream);
-    runIvfScatter(rowsDev, idsDev, assignDev, offsets.as<int>(), n, codeSize_, dStart_, codes_, ids_, stream);
+    if (interleaved_)
+        runIvfPqScatterInterleaved(rowsDev, idsDev, assignDev, offsets.as<int>(), n, codeSize_, dStart_, codes_, ids_, stream);
+    else
+        runIvfScatter(rowsDev, idsDev, assignDev, offsets.as<int>(), n, codeSize_, dStart_, codes_, ids_, stream);
     for (int64_t l = 0; l < nlist_; l++)
         hLen_[l] += hc[l];
     CUDA_VERIFY(cudaMemcpyAsync(dLen_, hLen_.data(), sizeof(int) * nlist_, cudaMemcpyHostToDevice, stream));
@@ -803,7 +816,14 @@ void IvfLists::setListFromHost(int64_t l, int64_t len, const uint8_t* codes, con
         relayout_(cap, stream);
     }
     if (len > 0) {
-        CUDA_VERIFY(cudaMemcpyAsync(codes_ + hStart_[l] * codeSize_, codes, (size_t)len * codeSize_, cudaMemcpyDefault, stream));
+        if (interleaved_) {
+            auto tmp = res_->temp(device_, (size_t)len * codeSize_);
+            CUDA_VERIFY(cudaMemcpyAsync(tmp.data, codes, (size_t)len * codeSize_, cudaMemcpyDefault, stream));
+            runIvfPqListToInterleaved(tmp.as<uint8_t>(), len, codeSize_, codes_ + hStart_[l] * codeSize_, stream);
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+        } else {
+            CUDA_VERIFY(cudaMemcpyAsync(codes_ + hStart_[l] * codeSize_, codes, (size_t)len * codeSize_, cudaMemcpyDefault, stream));
+        }
         CUDA_VERIFY(cudaMemcpyAsync(ids_ + hStart_[l], ids, (size_t)len * sizeof(idx_t), cudaMemcpyDefault, stream));
     }
     hLen_[l] = (int)len;
@@ -816,8 +836,16 @@ void IvfLists::getListToHost(int64_t l, uint8_t* codes, idx_t* ids, cudaStream_t
     int64_t len = hLen_[l];
     if (len == 0)
         return;
-    if (codes)
-        CUDA_VERIFY(cudaMemcpyAsync(codes, codes_ + hStart_[l] * codeSize_, (size_t)len * codeSize_, cudaMemcpyDeviceToHost, stream));
+    if (codes) {
+        if (interleaved_) {
+            auto tmp = res_->temp(device_, (size_t)len * codeSize_);
+            runIvfPqListFromInterleaved(codes_ + hStart_[l] * codeSize_, len, codeSize_, tmp.as<uint8_t>(), stream);
+            CUDA_VERIFY(cudaMemcpyAsync(codes, tmp.data, (size_t)len * codeSize_, cudaMemcpyDeviceToHost, stream));
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+        } else {
+            CUDA_VERIFY(cudaMemcpyAsync(codes, codes_ + hStart_[l] * codeSize_, (size_t)len * codeSize_, cudaMemcpyDeviceToHost, stream));
+        }
+    }
     if (ids)
         CUDA_VERIFY(cudaMemcpyAsync(ids, ids_ + hStart_[l], (size_t)len * sizeof(idx_t), cudaMemcpyDeviceToHost, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
@@ -832,7 +860,8 @@ GpuIndexIVF::GpuIndexIVF(
         MetricType metric,
         idx_t nlist_,
         int codeSize,
-        GpuIndexIVFConfig config)
+        GpuIndexIVFConfig config,
+        bool pqInterleaved)
         : GpuIndex(std::move(resources), dims, metric, 0, config), nlist(nlist_), ivfConfig_(config) {
     FB_THROW_IF_NOT_MSG(nlist > 0, "nlist must be > 0");
     // faiss/gpu/GpuIndexIVF.cu:78-80
@@ -842,7 +871,7 @@ GpuIndexIVF::GpuIndexIVF(
     quantizer = new GpuIndexFlat(resources_, dims, metric, fc);
     own_fields = true;
     this->is_trained = false;
-    lists_.reset(new IvfLists(resources_.get(), config.device, nlist, codeSize));
+    lists_.reset(new IvfLists(resources_.get(), config.device, nlist, codeSize, pqInterleaved));
 }
 
 GpuIndexIVF::~GpuIndexIVF() {
@@ -1022,11 +1051,19 @@ GpuIndexIVFPQ::GpuIndexIVFPQ(
         idx_t bitsPerCode,
         MetricType metric,
         GpuIndexIVFPQConfig config)
-        : GpuIndexIVF(std::move(resources), dims, metric, nlist, (int)subQuantizers, config),
+        : GpuIndexIVF(
+                  std::move(resources),
+                  dims,
+                  metric,
+                  nlist,
+                  (int)subQuantizers,
+                  config,
+                  ivfPqInterleavedSupported((int)subQuantizers) && bitsPerCode == 8),
           M_((int)subQuantizers),
           nbits_((int)bitsPerCode),
           usePrecomputed_(config.usePrecomputedTables),
-          pqCentroids_(resources_.get(), config.device, AllocType::Quantizer) {
+          pqCentroids_(resources_.get(), config.device, AllocType::Quantizer),
+          pqCentroidsT_(resources_.get(), config.device, AllocType::Quantizer) {
     // faiss/gpu/GpuIndexIVFPQ.cu:124-131, verifyPQSettings_ :596-617
     FB_THROW_IF_NOT_MSG(bitsPerCode == 8, "GPU: only pq.nbits == 8 is supported");
     FB_THROW_IF_NOT_MSG(subQuantizers > 0 && dims % subQuantizers == 0,
@@ -1045,6 +1082,16 @@ void GpuIndexIVFPQ::setPQCentroids(const float* c) {
     auto stream = stream_();
     pqCentroids_.resize((size_t)256 * d, stream);
     CUDA_VERIFY(cudaMemcpyAsync(pqCentroids_.data(), c, sizeof(float) * 256 * d, cudaMemcpyDefault, stream));
+    // transposed copy [256][M][dsub]
+    std::vector<float> h((size_t)256 * d), ht((size_t)256 * d);
+    CUDA_VERIFY(cudaMemcpyAsync(h.data(), pqCentroids_.data(), sizeof(float) * 256 * d, cudaMemcpyDeviceToHost, stream));
+    CUDA_VERIFY(cudaStreamSynchronize(stream));
+    const int dsub = d / M_;
+    for (int m = 0; m < M_; m++)
+        for (int cc = 0; cc < 256; cc++)
+            memcpy(&ht[((size_t)cc * M_ + m) * dsub], &h[((size_t)m * 256 + cc) * dsub], sizeof(float) * dsub);
+    pqCentroidsT_.resize((size_t)256 * d, stream);
+    CUDA_VERIFY(cudaMemcpyAsync(pqCentroidsT_.data(), ht.data(), sizeof(float) * 256 * d, cudaMemcpyHostToDevice, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
 }
 
@@ -1143,6 +1190,13 @@ void GpuIndexIVFPQ::scanImpl_(
         float* dDev,
         idx_t* iDev) const {
     FB_THROW_IF_NOT_MSG(pqCentroids_.size() > 0, "PQ not trained");
+    if (lists_->interleaved()) {
+        runIvfPqScanInterleaved(
+                resources_.get(), config_.device, xDev, n, d, probes, coarseDis, np, quantizer->vectorsDevice(),
+                pqCentroidsT_.data(), M_, lists_->dStart(), lists_->dLen(), lists_->codes(), lists_->ids(), k,
+                metric_type, dDev, iDev, stream_());
+        return;
+    }
     runIvfPqScan(
             resources_.get(), config_.device, xDev, n, d, probes, coarseDis, np, quantizer->vectorsDevice(),
             pqCentroids_.data(), M_, lists_->dStart(), lists_->dLen(), lists_->codes(), lists_->ids(), k, metric_type,

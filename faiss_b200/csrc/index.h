@@ -290,7 +290,9 @@ int split_clusters(size_t d, size_t k, size_t n, float* hassign, float* centroid
 // ------------------------------------------------------------------------------------------
 class IvfLists {
    public:
-    IvfLists(GpuResources* res, int device, int64_t nlist, int codeSize);
+    // pqInterleaved: store codes in the rotated, interleaved-by-32 PQ layout (kernels.h); the
+    // host-facing accessors below always speak the flat [len][codeSize] ArrayInvertedLists format
+    IvfLists(GpuResources* res, int device, int64_t nlist, int codeSize, bool pqInterleaved = false);
     ~IvfLists();
     void reset();
     void reserve(size_t totalVecs, cudaStream_t stream);
@@ -324,6 +326,9 @@ class IvfLists {
         return codeSize_;
     }
     int maxListLength() const;
+    bool interleaved() const {
+        return interleaved_;
+    }
 
    private:
     void relayout_(const std::vector<int64_t>& newCap, cudaStream_t stream);
@@ -333,6 +338,7 @@ class IvfLists {
     int device_;
     int64_t nlist_;
     int codeSize_;
+    bool interleaved_ = false;
     uint8_t* codes_ = nullptr;
     idx_t* ids_ = nullptr;
     int64_t arenaElems_ = 0;
@@ -362,7 +368,8 @@ class GpuIndexIVF : public GpuIndex {
             MetricType metric,
             idx_t nlist,
             int codeSize,
-            GpuIndexIVFConfig config);
+            GpuIndexIVFConfig config,
+            bool pqInterleaved = false);
     ~GpuIndexIVF() override;
 
     idx_t nlist;
@@ -481,7 +488,8 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
 
     int M_, nbits_;
     bool usePrecomputed_ = false;
-    DeviceVector<float> pqCentroids_;
+    DeviceVector<float> pqCentroids_;  // [M][256][dsub]
+    DeviceVector<float> pqCentroidsT_; // [256][M][dsub] (LUT build reads it coalesced)
 };
 
 // ------------------------------------------------------------------------------------------

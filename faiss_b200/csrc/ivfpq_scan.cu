@@ -1,0 +1,340 @@
+// faiss_b200 -- IVF-PQ scan over the rotated, interleaved-by-32 code layout (see kernels.h).
+//
+// What it replaces: pqCodeDistances (LUT [nq,nprobe,M,256] written to HBM,
+// faiss/gpu/impl/PQCodeDistances-inl.cuh:34-285) + pqScanNoPrecomputedMultiPass (per-thread 32-byte
+// strided code loads, every distance written to HBM, PQScanMultiPassNoPrecomputed-inl.cuh:174-270,
+// PQCodeLoad.cuh:439-454) + pass1/pass2SelectLists (IVFUtilsSelect1/2.cu).
+//
+// Bound: HBM (codes: M bytes per scanned vector), co-limited by shared-memory gathers (M lookups per
+// vector).  Both limits are attacked by the layout:
+//   * a warp reads a 32-vector group as M/16 fully coalesced 512-byte loads;
+//   * per lookup the inner loop is PRMT (byte -> LUT row address | lane slot) + LDS + FADD, and the
+//     LUT access is bank-conflict-free by construction (lane t reads bank (t + j) % 32).
+// LUT and distances never touch HBM; the running top-k stays in shared memory (select.cuh).
+#include <cfloat>
+
+#include "kernels.h"
+#include "select.cuh"
+
+namespace fb200 {
+
+void runMergeTopKKeyspace(
+        const float*, const idx_t*, int64_t, int, int, int, MetricType, int64_t, float*, idx_t*, cudaStream_t);
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kBuf = 64;
+constexpr int kLutSlots = 64; // 256 B per code value
+
+__device__ __forceinline__ int64_t interleaved_pos(int64_t v, int j, int M) {
+    // byte position j of list-relative vector v
+    const int64_t g = v >> 5;
+    const int t = (int)(v & 31);
+    return g * 32 * M + (j >> 4) * 512 + t * 16 + (j & 15);
+}
+
+__global__ void pq_scatter_interleaved_kernel(
+        const uint8_t* __restrict__ flat,
+        const idx_t* __restrict__ ids,
+        const idx_t* __restrict__ assign,
+        const int* __restrict__ offsets,
+        int64_t n,
+        int M,
+        const int64_t* __restrict__ listStart,
+        uint8_t* __restrict__ arenaCodes,
+        idx_t* __restrict__ arenaIds) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n)
+        return;
+    const int off = offsets[i];
+    if (off < 0)
+        return;
+    const int64_t ls = listStart[assign[i]];
+    uint8_t* base = arenaCodes + ls * M;
+    const int t = off & 31;
+    for (int j = lane_id(); j < M; j += 32)
+        base[interleaved_pos(off, j, M)] = flat[i * M + ((j + t) % M)];
+    if (lane_id() == 0)
+        arenaIds[ls + off] = ids[i];
+}
+
+__global__ void pq_list_to_interleaved_kernel(const uint8_t* __restrict__ flat, int64_t len, int M, uint8_t* __restrict__ dst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len * M)
+        return;
+    const int64_t v = e / M;
+    const int j = (int)(e - v * M);
+    dst[interleaved_pos(v, j, M)] = flat[v * M + ((j + (int)(v & 31)) % M)];
+}
+
+__global__ void pq_list_from_interleaved_kernel(const uint8_t* __restrict__ src, int64_t len, int M, uint8_t* __restrict__ flat) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len * M)
+        return;
+    const int64_t v = e / M;
+    const int j = (int)(e - v * M);
+    flat[v * M + ((j + (int)(v & 31)) % M)] = src[interleaved_pos(v, j, M)];
+}
+
+// block-level merge of the per-warp lists into warp 0 + write-out (same contract as ivf.cu)
+__device__ void merge_and_write(
+        WarpTopK<int>& w,
+        int warp,
+        unsigned char* lists,
+        size_t perWarp,
+        int LIST,
+        int k,
+        const idx_t* __restrict__ ids,
+        float addToKey,
+        float* __restrict__ outD,
+        idx_t* __restrict__ outI) {
+    w.finish();
+    __syncthreads();
+    if (warp == 0) {
+        for (int ow = 1; ow < kWarps; ow++) {
+            const float* ok = reinterpret_cast<const float*>(lists + perWarp * ow);
+            const int* oi = reinterpret_cast<const int*>(lists + perWarp * ow + sizeof(float) * (LIST + kBuf));
+            for (int e0 = 0; e0 < k; e0 += 32) {
+                int e = e0 + lane_id();
+                bool valid = e < k;
+                float key = valid ? ok[e] : 0.f;
+                int id = valid ? oi[e] : 0;
+                valid = valid && id != IdLimits<int>::max();
+                if (!__any_sync(kFullMask, valid && key <= w.thr))
+                    break;
+                w.add(valid, key, id);
+            }
+        }
+        w.finish();
+        for (int j = lane_id(); j < k; j += 32) {
+            int id = w.q.ids[j];
+            bool ok2 = id != IdLimits<int>::max();
+            outD[j] = ok2 ? w.q.keys[j] + addToKey : CUDART_INF_F;
+            outI[j] = ok2 ? ids[id] : -1;
+        }
+    }
+}
+
+template <int M, bool IS_L2>
+__global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
+        const float* __restrict__ Q,
+        int d,
+        const idx_t* __restrict__ probes,
+        const float* __restrict__ coarseDis,
+        int nprobe,
+        const float* __restrict__ coarse,
+        const float* __restrict__ pqT, // [256][M][dsub]
+        const int64_t* __restrict__ listStart,
+        const int* __restrict__ listLen,
+        const uint8_t* __restrict__ arenaCodes,
+        const idx_t* __restrict__ arenaIds,
+        int k,
+        int LIST,
+        float* __restrict__ partD,
+        idx_t* __restrict__ partI) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int q = blockIdx.y, p = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int dsub = d / M;
+    float* lut = reinterpret_cast<float*>(smem_raw);                 // [256][kLutSlots]
+    float* rs = lut + 256 * kLutSlots;                               // [d]
+    unsigned char* lists = reinterpret_cast<unsigned char*>(rs) + round_up(sizeof(float) * d, 16);
+    const size_t perWarp = SmemTopK<int>::bytes(LIST, kBuf);
+    float* oD = partD + ((int64_t)q * nprobe + p) * k;
+    idx_t* oI = partI + ((int64_t)q * nprobe + p) * k;
+
+    const idx_t l = probes[(int64_t)q * nprobe + p];
+    if (l < 0) {
+        for (int j = threadIdx.x; j < k; j += blockDim.x) {
+            oD[j] = CUDART_INF_F;
+            oI[j] = -1;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        float v = Q[(int64_t)q * d + i];
+        rs[i] = IS_L2 ? v - coarse[l * d + i] : v;
+    }
+    WarpTopK<int> w;
+    unsigned char* mine = lists + perWarp * warp;
+    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<int*>(mine + sizeof(float) * (LIST + kBuf)), LIST, kBuf, k);
+    __syncthreads();
+    // ---- LUT: entry (c, m) -> slots m, m+M, ... (< 64).  e = c*M + m: coalesced pqT reads, conflict-free writes
+    for (int e = threadIdx.x; e < 256 * M; e += blockDim.x) {
+        const int c = e / M, m = e - c * M;
+        const float* cp = pqT + (size_t)e * dsub;
+        const float* rp = rs + m * dsub;
+        float acc = 0.f;
+        for (int j = 0; j < dsub; j++) {
+            if (IS_L2) {
+                float df = rp[j] - cp[j];
+                acc = fmaf(df, df, acc);
+            } else {
+                acc = fmaf(rp[j], cp[j], acc);
+            }
+        }
+        const float val = IS_L2 ? acc : -acc;
+#pragma unroll
+        for (int s = 0; s < kLutSlots; s += M)
+            lut[c * kLutSlots + s + m] = val;
+    }
+    __syncthreads();
+
+    const int len = listLen[l];
+    const uint8_t* codes = arenaCodes + listStart[l] * (int64_t)M;
+    const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
+    const unsigned lane4 = (unsigned)lane << 2;
+    const int ngroups = (len + 31) >> 5;
+    for (int g = warp; g < ngroups; g += kWarps) {
+        const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+        uint4 c4[M / 16];
+#pragma unroll
+        for (int h = 0; h < M / 16; h++)
+            c4[h] = __ldg(gp + h * 32);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int h = 0; h < M / 16; h++) {
+            const unsigned wds[4] = {c4[h].x, c4[h].y, c4[h].z, c4[h].w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int j = h * 16 + wi * 4 + b;
+                    // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
+                    const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
+                    const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
+                    if (j & 1)
+                        a1 += val;
+                    else
+                        a0 += val;
+                }
+            }
+        }
+        const int v = g * 32 + lane;
+        w.add(v < len, a0 + a1, v);
+    }
+    const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
+    merge_and_write(w, warp, lists, perWarp, LIST, k, arenaIds + listStart[l], add, oD, oI);
+}
+
+} // namespace
+
+void runIvfPqScatterInterleaved(
+        const uint8_t* codesFlat,
+        const idx_t* ids,
+        const idx_t* assign,
+        const int* offsets,
+        int64_t n,
+        int M,
+        const int64_t* listStart,
+        uint8_t* arenaCodes,
+        idx_t* arenaIds,
+        cudaStream_t stream) {
+    if (n == 0)
+        return;
+    int warps = 8;
+    pq_scatter_interleaved_kernel<<<(unsigned)ceil_div(n, warps), warps * 32, 0, stream>>>(
+            codesFlat, ids, assign, offsets, n, M, listStart, arenaCodes, arenaIds);
+    CUDA_CHECK_LAST();
+}
+
+void runIvfPqListToInterleaved(const uint8_t* flat, int64_t len, int M, uint8_t* listCodes, cudaStream_t stream) {
+    if (len == 0)
+        return;
+    pq_list_to_interleaved_kernel<<<(unsigned)ceil_div(len * M, 256), 256, 0, stream>>>(flat, len, M, listCodes);
+    CUDA_CHECK_LAST();
+}
+
+void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, uint8_t* flat, cudaStream_t stream) {
+    if (len == 0)
+        return;
+    pq_list_from_interleaved_kernel<<<(unsigned)ceil_div(len * M, 256), 256, 0, stream>>>(listCodes, len, M, flat);
+    CUDA_CHECK_LAST();
+}
+
+template <int M, bool IS_L2>
+static void launchScan(
+        dim3 grid,
+        size_t smem,
+        cudaStream_t stream,
+        const float* Q,
+        int d,
+        const idx_t* probes,
+        const float* coarseDis,
+        int nprobe,
+        const float* coarse,
+        const float* pqT,
+        const int64_t* listStart,
+        const int* listLen,
+        const uint8_t* codes,
+        const idx_t* ids,
+        int k,
+        int LIST,
+        float* partD,
+        idx_t* partI) {
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2>;
+    CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KernelTiming::begin("ivfpq_scan", stream);
+    kern<<<grid, kWarps * 32, smem, stream>>>(
+            Q, d, probes, coarseDis, nprobe, coarse, pqT, listStart, listLen, codes, ids, k, LIST, partD, partI);
+    KernelTiming::end("ivfpq_scan", stream);
+    CUDA_CHECK_LAST();
+}
+
+void runIvfPqScanInterleaved(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        int d,
+        const idx_t* probes,
+        const float* coarseDis,
+        int nprobe,
+        const float* coarseCentroids,
+        const float* pqCentroidsT,
+        int M,
+        const int64_t* listStart,
+        const int* listLen,
+        const uint8_t* arenaCodes,
+        const idx_t* arenaIds,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream) {
+    if (nq == 0)
+        return;
+    FB_THROW_IF_NOT(ivfPqInterleavedSupported(M));
+    const int LIST = std::max(64, next_pow2(k));
+    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + SmemTopK<int>::bytes(LIST, kBuf) * kWarps;
+    FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
+    const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)nprobe * k * 12)));
+    const bool l2 = metric == METRIC_L2;
+    for (int64_t q0 = 0; q0 < nq; q0 += maxQ) {
+        int64_t nb = std::min(maxQ, nq - q0);
+        auto partD = res->temp(device, sizeof(float) * nb * nprobe * k);
+        auto partI = res->temp(device, sizeof(idx_t) * nb * nprobe * k);
+        dim3 grid((unsigned)nprobe, (unsigned)nb);
+#define SCAN(M_, L2_)                                                                                              \
+    launchScan<M_, L2_>(                                                                                           \
+            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, coarseCentroids, \
+            pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(), partI.as<idx_t>())
+        if (M == 32) {
+            if (l2)
+                SCAN(32, true);
+            else
+                SCAN(32, false);
+        } else {
+            if (l2)
+                SCAN(16, true);
+            else
+                SCAN(16, false);
+        }
+#undef SCAN
+        runMergeTopKKeyspace(
+                partD.as<float>(), partI.as<idx_t>(), nb, nprobe, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
+    }
+}
+
+} // namespace fb200

