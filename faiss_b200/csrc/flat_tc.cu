@@ -28,6 +28,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -71,6 +72,7 @@ struct TcParams {
     float* dump;        // debug: raw accumulators [nq][dumpLd]
     long long dumpLd;
     int nq;
+    int debugSkip;      // timing experiments only: 1 = skip the filter (TMEM loads still issued)
 };
 
 __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
@@ -101,23 +103,35 @@ __device__ __forceinline__ void epi_filter32(
         return;
     }
     float v[32];
-    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+    // four independent max chains, one per group of 8 consecutive columns
+    float mg[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float4 b = ptx::lds128(bp + j * 16);
-        ptx::fma2(v[4 * j], v[4 * j + 1], __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), inv, b.x, b.y);
-        ptx::fma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]), inv, b.z, b.w);
-        m0 = ptx::max3(m0, v[4 * j], v[4 * j + 1]);
-        m1 = ptx::max3(m1, v[4 * j + 2], v[4 * j + 3]);
+    for (int g = 0; g < 4; g++) {
+        const float4 b0 = ptx::lds128(bp + (2 * g) * 16);
+        const float4 b1 = ptx::lds128(bp + (2 * g + 1) * 16);
+        const int o = 8 * g;
+        ptx::fma2(v[o + 0], v[o + 1], __uint_as_float(r[o + 0]), __uint_as_float(r[o + 1]), inv, b0.x, b0.y);
+        ptx::fma2(v[o + 2], v[o + 3], __uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]), inv, b0.z, b0.w);
+        ptx::fma2(v[o + 4], v[o + 5], __uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]), inv, b1.x, b1.y);
+        ptx::fma2(v[o + 6], v[o + 7], __uint_as_float(r[o + 6]), __uint_as_float(r[o + 7]), inv, b1.z, b1.w);
+        const float a = ptx::max3(v[o + 0], v[o + 1], v[o + 2]);
+        const float c = ptx::max3(v[o + 3], v[o + 4], v[o + 5]);
+        mg[g] = ptx::max3(a, c, fmaxf(v[o + 6], v[o + 7]));
     }
-    if (fmaxf(m0, m1) > thr) {
+    if (ptx::max3(mg[0], mg[1], fmaxf(mg[2], mg[3])) > thr) {
+        // rare: walk only the groups that hold a survivor
         const unsigned rowBase = (unsigned)colBase;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            if (v[j] > thr) {
-                if (cnt < p.cap)
-                    buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
-                cnt++;
+        for (int g = 0; g < 4; g++) {
+            if (mg[g] > thr) {
+#pragma unroll
+                for (int j = 8 * g; j < 8 * g + 8; j++) {
+                    if (v[j] > thr) {
+                        if (cnt < p.cap)
+                            buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
+                        cnt++;
+                    }
+                }
             }
         }
     }
@@ -289,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                 const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * 64);
                 ptx::tmem_ld_wait(); // A landed
                 ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN + 32), rb);
-                epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
+                if (!p.debugSkip)
+                    epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
                 ptx::tmem_ld_wait(); // B landed: the accumulator stage can go back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -304,7 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     ptx::tc_fence_after();
                     ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), ra);
                 }
-                epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
+                if (!p.debugSkip)
+                    epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
                 __syncwarp();
                 if (lane == 0)
                     ptx::mbar_arrive(&b_empty[bs]);
@@ -452,10 +468,13 @@ __global__ void tc_select_kernel(
     // note: selection keeps the LIST best (k = LIST for the queue threshold)
     const float* bk = baseKey + (int64_t)q * LIST;
     const int* bi = baseId + (int64_t)q * LIST;
+    // the base list is already sorted (sentinels last): adopt it as the queue's list
     for (int e0 = 0; e0 < LIST; e0 += 32) {
-        int id = bi[e0 + lane];
-        w.add(id != IdLimits<int>::max(), bk[e0 + lane], id);
+        w.q.keys[e0 + lane] = bk[e0 + lane];
+        w.q.ids[e0 + lane] = bi[e0 + lane];
     }
+    __syncwarp();
+    w.thr = w.q.threshold();
     int overflow = 0;
     const int qt = q / kTileM, row = q % kTileM;
     for (int s = 0; s < slices; s++) {
@@ -536,7 +555,26 @@ __global__ void tc_rerank_kernel(
         float acc = 0.f;
         if (valid) {
             const float* yp = Y + (int64_t)id * d;
-            for (int i = 0; i < d; i++) {
+            // canonical order: sequential FMA over the dimension (loads vectorised, math not reordered)
+            int i = 0;
+            if ((d & 3) == 0) {
+                for (; i < d; i += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(qp + i);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(yp + i));
+                    const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (IS_L2) {
+                            float df = aa[u] - bb[u];
+                            acc = fmaf(df, df, acc);
+                        } else {
+                            acc = fmaf(aa[u], bb[u], acc);
+                        }
+                    }
+                }
+            }
+            for (; i < d; i++) {
                 float a = qp[i], b = yp[i];
                 if (IS_L2) {
                     float df = a - b;
@@ -864,7 +902,14 @@ void runFlatTcSearch(
         {
             int64_t seen = 0;
             while (seen < T) {
-                int64_t end = seen == 0 ? std::min<int64_t>(T, 32) : std::min<int64_t>(T, seen * 4);
+                // schedule knobs (tuning only): first-round tiles, early / late growth factors
+                static const int r0Tiles = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 32;
+                static const double gEarly = getenv("FB200_TC_G_EARLY") ? atof(getenv("FB200_TC_G_EARLY")) : 4.0;
+                static const double gLate = getenv("FB200_TC_G_LATE") ? atof(getenv("FB200_TC_G_LATE")) : 4.0;
+                static const int64_t lateFrom = getenv("FB200_TC_LATE_FROM") ? atol(getenv("FB200_TC_LATE_FROM")) : 8192;
+                const double g = seen >= lateFrom ? gLate : gEarly;
+                int64_t end = seen == 0 ? std::min<int64_t>(T, std::max(r0Tiles, (k + 127) / 128 * 2))
+                                        : std::min<int64_t>(T, (int64_t)(seen * g));
                 if (T - end < end / 4)
                     end = T; // do not leave a sliver for an extra round
                 int64_t tiles = end - seen;
@@ -931,6 +976,7 @@ void runFlatTcSearch(
             p.dump = nullptr;
             p.dumpLd = 0;
             p.nq = (int)nq;
+            p.debugSkip = getenv("FB200_TC_DEBUG_SKIP") ? atoi(getenv("FB200_TC_DEBUG_SKIP")) : 0;
             launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
