@@ -35,6 +35,7 @@
 #include "kernels.h"
 #include "select.cuh"
 #include "tc_ptx.cuh"
+#include "flat_tc_kernel.cuh"
 
 namespace fb200 {
 
@@ -43,304 +44,7 @@ void runMergeTopKKeyspace(
 
 namespace {
 
-constexpr int kTileM = 128;       // queries per tile (TMEM lanes)
-constexpr int kTileN = 128;       // database rows per tile (TMEM columns per accumulator stage)
-constexpr int kAccStages = 4;     // 4 x 128 columns = 512 TMEM columns
-constexpr int kKBlock = 64;       // fp16 elements per 128-byte swizzle row
-constexpr int kKBlockBytes = kTileN * kKBlock * 2; // 16 KiB per (128 rows x 64 halfs)
-constexpr int kThreads = 320;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int kEpiWarps = 8;
-constexpr int kMaxYStages = 6;
-constexpr int kBiasSlots = 8;     // per-tile bias (512 B) + tile id ring, producer -> epilogue
-
-struct TcParams {
-    int numUnits;
-    int slices;
-    int qTiles;         // unit u = slice * qTiles + queryTile: neighbouring CTAs stream the SAME database tiles (L2 reuse)
-    int tileBegin;      // permuted position range of this round
-    int tileEnd;
-    int tilesPerSlice;
-    unsigned long long permA, permB, numTiles;
-    int KB;             // dpad / 64
-    int yStages;
-    const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
-    const float* bias;  // [numTiles*128], -inf padded
-    const float* thr;   // [nq]  pass if score > thr
-    uint2* cand;        // [numUnits*256][cap] (score bits, row)
-    int cap;
-    int* candCount;     // [numUnits*256]
-    float* dump;        // debug: raw accumulators [nq][dumpLd]
-    long long dumpLd;
-    int nq;
-    int debugSkip;      // timing experiments only: 1 = skip the filter (TMEM loads still issued)
-};
-
-__device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
-    return (int)(((unsigned long long)pos * p.permA + p.permB) % p.numTiles);
-}
-
-// Filter 32 columns of this thread's query row: score = acc * inv + bias, chunk maximum against the
-// query's threshold; the rare survivors are appended to the thread-private candidate segment.
-// FFMA2 + FMNMX3: one instruction per element.
-template <bool DUMP>
-__device__ __forceinline__ void epi_filter32(
-        const TcParams& p,
-        const uint32_t (&r)[32],
-        int q,
-        long long colBase, // global row index of column 0 of this chunk
-        float inv,
-        float thr,
-        uint32_t bp, // shared address of the 32 biases
-        uint2* buf,
-        int& cnt) {
-    if (DUMP) {
-        if (q < p.nq) {
-            float* dst = p.dump + (long long)q * p.dumpLd + colBase;
-#pragma unroll
-            for (int j = 0; j < 32; j++)
-                dst[j] = __uint_as_float(r[j]);
-        }
-        return;
-    }
-    float v[32];
-    // four independent max chains, one per group of 8 consecutive columns
-    float mg[4];
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-        const float4 b0 = ptx::lds128(bp + (2 * g) * 16);
-        const float4 b1 = ptx::lds128(bp + (2 * g + 1) * 16);
-        const int o = 8 * g;
-        ptx::fma2(v[o + 0], v[o + 1], __uint_as_float(r[o + 0]), __uint_as_float(r[o + 1]), inv, b0.x, b0.y);
-        ptx::fma2(v[o + 2], v[o + 3], __uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]), inv, b0.z, b0.w);
-        ptx::fma2(v[o + 4], v[o + 5], __uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]), inv, b1.x, b1.y);
-        ptx::fma2(v[o + 6], v[o + 7], __uint_as_float(r[o + 6]), __uint_as_float(r[o + 7]), inv, b1.z, b1.w);
-        const float a = ptx::max3(v[o + 0], v[o + 1], v[o + 2]);
-        const float c = ptx::max3(v[o + 3], v[o + 4], v[o + 5]);
-        mg[g] = ptx::max3(a, c, fmaxf(v[o + 6], v[o + 7]));
-    }
-    if (ptx::max3(mg[0], mg[1], fmaxf(mg[2], mg[3])) > thr) {
-        // rare: walk only the groups that hold a survivor
-        const unsigned rowBase = (unsigned)colBase;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            if (mg[g] > thr) {
-#pragma unroll
-                for (int j = 8 * g; j < 8 * g + 8; j++) {
-                    if (v[j] > thr) {
-                        if (cnt < p.cap)
-                            buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
-                        cnt++;
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <bool DUMP>
-__global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
-        const __grid_constant__ CUtensorMap mapQ,
-        const __grid_constant__ CUtensorMap mapY,
-        const TcParams p) {
-    extern __shared__ unsigned char smem_dyn[];
-    // 1024-byte aligned carve-up (SWIZZLE_128B atoms need it)
-    unsigned char* smem = reinterpret_cast<unsigned char*>(
-            (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const int stageBytes = p.KB * kKBlockBytes;
-    unsigned char* sQ = smem;
-    unsigned char* sY = smem + stageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sY + (size_t)p.yStages * stageBytes);
-    uint64_t* q_full = bars + 0;
-    uint64_t* q_empty = bars + 1;
-    uint64_t* y_full = bars + 2;
-    uint64_t* y_empty = y_full + kMaxYStages;
-    uint64_t* t_full = y_empty + kMaxYStages;
-    uint64_t* t_empty = t_full + kAccStages;
-    uint64_t* b_full = t_empty + kAccStages;
-    uint64_t* b_empty = b_full + kBiasSlots;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kBiasSlots);
-    int* tileS = reinterpret_cast<int*>(tmem_slot + 2);                         // [kBiasSlots]
-    float* biasS = reinterpret_cast<float*>(tileS + kBiasSlots + 2);            // [kBiasSlots][128], 16B aligned
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&mapQ);
-        ptx::prefetch_tensormap(&mapY);
-        ptx::mbar_init(q_full, 1);
-        ptx::mbar_init(q_empty, 1);
-        for (int i = 0; i < p.yStages; i++) {
-            ptx::mbar_init(&y_full[i], 1);
-            ptx::mbar_init(&y_empty[i], 1);
-        }
-        for (int i = 0; i < kAccStages; i++) {
-            ptx::mbar_init(&t_full[i], 1);
-            ptx::mbar_init(&t_empty[i], kEpiWarps);
-        }
-        for (int i = 0; i < kBiasSlots; i++) {
-            ptx::mbar_init(&b_full[i], 1);
-            ptx::mbar_init(&b_empty[i], kEpiWarps);
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 1) {
-        ptx::tmem_alloc<512>(tmem_slot);
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            int ys = 0, bs = 0;
-            uint32_t yphase = 0, bphase = 0;
-            int it = 0;
-            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
-                const int qt = u % p.qTiles;
-                const int sl = u / p.qTiles;
-                ptx::mbar_wait(q_empty, (it & 1) ^ 1);
-                ptx::mbar_arrive_expect_tx(q_full, (uint32_t)stageBytes);
-                ptx::tma_load_3d(sQ, &mapQ, q_full, 0, qt * kTileM, 0);
-                const int pb = p.tileBegin + sl * p.tilesPerSlice;
-                const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
-                for (int pp = pb; pp < pe; pp++) {
-                    const int t = perm_tile(p, pp);
-                    ptx::mbar_wait(&y_empty[ys], yphase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&y_full[ys], (uint32_t)stageBytes);
-                    ptx::tma_load_3d(sY + (size_t)ys * stageBytes, &mapY, &y_full[ys], 0, t * kTileN, 0);
-                    if (++ys == p.yStages) {
-                        ys = 0;
-                        yphase ^= 1;
-                    }
-                    // per-tile bias + tile id for the epilogue
-                    ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-                    ptx::sts32(ptx::smem_u32(tileS + bs), t);
-                    ptx::mbar_arrive_expect_tx(&b_full[bs], kTileN * 4);
-                    ptx::bulk_load_1d(biasS + bs * kTileN, p.bias + (long long)t * kTileN, kTileN * 4, &b_full[bs]);
-                    if (++bs == kBiasSlots) {
-                        bs = 0;
-                        bphase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
-            int ys = 0, as = 0;
-            uint32_t yphase = 0, aphase = 0;
-            int it = 0;
-            const uint32_t sQaddr = ptx::smem_u32(sQ);
-            const uint32_t sYaddr = ptx::smem_u32(sY);
-            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
-                const int sl = u / p.qTiles;
-                const int pb = p.tileBegin + sl * p.tilesPerSlice;
-                const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
-                ptx::mbar_wait(q_full, it & 1);
-                ptx::tc_fence_after();
-                for (int pp = pb; pp < pe; pp++) {
-                    ptx::mbar_wait(&t_empty[as], aphase ^ 1);
-                    ptx::mbar_wait(&y_full[ys], yphase);
-                    ptx::tc_fence_after();
-                    const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
-                    const uint32_t dcol = tmem_base + (uint32_t)as * kTileN;
-                    for (int kb = 0; kb < p.KB; kb++) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; k4++) {
-                            uint64_t da = ptx::make_smem_desc_sw128(sQaddr + kb * kKBlockBytes + k4 * 32);
-                            uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * kKBlockBytes + k4 * 32);
-                            ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        }
-                    }
-                    ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
-                    ptx::mma_commit(&t_full[as]);  // accumulator stage ready for the epilogue
-                    if (++ys == p.yStages) {
-                        ys = 0;
-                        yphase ^= 1;
-                    }
-                    if (++as == kAccStages) {
-                        as = 0;
-                        aphase ^= 1;
-                    }
-                }
-                ptx::mma_commit(q_empty); // query tile may be overwritten
-            }
-        }
-    } else {
-        // ================================ epilogue ================================
-        const int ew = warp - 2;
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // which 64 columns of the tile
-        const int row = quarter * 32 + lane;
-        const float inv = *p.invScalePtr;
-        int as = 0, bs = 0;
-        uint32_t aphase = 0, bphase = 0;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
-        for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
-            const int qt = u % p.qTiles;
-            const int sl = u / p.qTiles;
-            const int q = qt * kTileM + row;
-            const float thr = (!DUMP && q < p.nq) ? p.thr[q] : CUDART_INF_F;
-            const long long seg = ((long long)u * kTileM + row) * 2 + half;
-            uint2* buf = DUMP ? nullptr : p.cand + seg * p.cap;
-            int cnt = 0;
-            const int pb = p.tileBegin + sl * p.tilesPerSlice;
-            const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
-            // Software pipeline at 32-column granularity: while chunk A (columns 0..31 of this warp's
-            // half) is filtered, the TMEM load of chunk B is in flight, and vice versa across tiles.
-            uint32_t ra[32], rb[32];
-            ptx::mbar_wait(&t_full[as], aphase);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), ra);
-            for (int pp = pb; pp < pe; pp++) {
-                ptx::mbar_wait(&b_full[bs], bphase);
-                const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
-                const long long colBase = (long long)t * kTileN + half * 64;
-                const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * 64);
-                ptx::tmem_ld_wait(); // A landed
-                ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN + 32), rb);
-                if (!p.debugSkip)
-                    epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
-                ptx::tmem_ld_wait(); // B landed: the accumulator stage can go back to the MMA warp
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&t_empty[as]);
-                if (++as == kAccStages) {
-                    as = 0;
-                    aphase ^= 1;
-                }
-                if (pp + 1 < pe) {
-                    ptx::mbar_wait(&t_full[as], aphase);
-                    ptx::tc_fence_after();
-                    ptx::tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(as * kTileN), ra);
-                }
-                if (!p.debugSkip)
-                    epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&b_empty[bs]);
-                if (++bs == kBiasSlots) {
-                    bs = 0;
-                    bphase ^= 1;
-                }
-            }
-            if (!DUMP)
-                p.candCount[seg] = cnt;
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc<512>(tmem_base);
-    }
-}
+using namespace tc;
 
 // ------------------------------------------------------------------------------------------
 // small helper kernels
@@ -476,11 +180,12 @@ __global__ void tc_select_kernel(
     __syncwarp();
     w.thr = w.q.threshold();
     int overflow = 0;
-    const int qt = q / kTileM, row = q % kTileM;
+    const int pair = q / kPairM, prow = q % kPairM; // row within the unit's 256 query rows
+    const int qPairs = (nq + kPairM - 1) / kPairM;
     for (int s = 0; s < slices; s++) {
-        const int u = s * ((nq + kTileM - 1) / kTileM) + qt;
+        const int u = s * qPairs + pair;
         for (int h = 0; h < 2; h++) {
-            const long long seg = ((long long)u * kTileM + row) * 2 + h;
+            const long long seg = ((long long)u * kPairM + prow) * 2 + h;
             int c = candCount[seg];
             if (c > cap) {
                 overflow = 1;
@@ -711,18 +416,18 @@ struct SmemPlan {
 SmemPlan planSmem(int KB) {
     const size_t stage = (size_t)KB * kKBlockBytes;
     const size_t budget = 220 * 1024;
-    const size_t fixed = 1024 /*align slack*/ + 512 /*barriers, tile ids*/ + kBiasSlots * kTileN * 4 /*bias ring*/ + stage /*Q*/;
+    const size_t fixed = 1024 /*align slack*/ + 512 /*barriers, tile ids*/ + kBiasSlots * kTileN * 4 /*bias ring*/;
     int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
     FB_THROW_IF_NOT_MSG(ys >= 2, "dimension too large for the tensor-core Flat kernel");
     return {ys, fixed + ys * stage};
 }
 
 template <bool DUMP>
-void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
+void launchTc(const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
     auto kern = flat_tc_kernel<DUMP>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("flat_tc", stream);
-    kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
+    kern<<<grid, kThreads, smem, stream>>>(my, p);
     KernelTiming::end("flat_tc", stream);
     CUDA_CHECK_LAST();
 }
@@ -779,10 +484,14 @@ void runFlatTcScoresDebug(
     FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= 256);
     const int KB = dpad / kKBlock;
     SmemPlan sp = planSmem(KB);
-    CUtensorMap mq = makeTileMap(Q16, nq, dpad);
     CUtensorMap my = makeTileMap(Y16, n, dpad);
     const int64_t numTiles = ceil_div(n, kTileN);
-    const int64_t qTiles = ceil_div(nq, kTileM);
+    const int64_t qPairs = ceil_div(nq, kPairM);
+    // the kernel reads whole 256-row query pairs: zero-padded private copy
+    __half* qpad = nullptr;
+    CUDA_VERIFY(cudaMallocAsync(&qpad, sizeof(__half) * qPairs * kPairM * dpad, stream));
+    CUDA_VERIFY(cudaMemsetAsync(qpad, 0, sizeof(__half) * qPairs * kPairM * dpad, stream));
+    CUDA_VERIFY(cudaMemcpyAsync(qpad, Q16, sizeof(__half) * nq * dpad, cudaMemcpyDeviceToDevice, stream));
     // bias (zeros) and scale (1.0) for the debug run
     float* bias = nullptr;
     float* one = nullptr;
@@ -793,8 +502,10 @@ void runFlatTcScoresDebug(
     CUDA_VERIFY(cudaMemcpyAsync(one, &h1, sizeof(float), cudaMemcpyHostToDevice, stream));
     TcParams p{};
     p.slices = 1;
-    p.qTiles = (int)qTiles;
-    p.numUnits = (int)qTiles;
+    p.qPairs = (int)qPairs;
+    p.numUnits = (int)qPairs;
+    p.Q16 = qpad;
+    p.accStages = (512 - dpad) / kTileN;
     p.tileBegin = 0;
     p.tileEnd = (int)numTiles;
     p.tilesPerSlice = (int)numTiles;
@@ -815,7 +526,8 @@ void runFlatTcScoresDebug(
     int dev = 0, sms = 0;
     CUDA_VERIFY(cudaGetDevice(&dev));
     CUDA_VERIFY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    launchTc<true>(mq, my, p, (int)std::min<int64_t>(p.numUnits, sms), sp.bytes, stream);
+    launchTc<true>(my, p, (int)std::min<int64_t>(p.numUnits, sms), sp.bytes, stream);
+    CUDA_VERIFY(cudaFreeAsync(qpad, stream));
     CUDA_VERIFY(cudaFreeAsync(bias, stream));
     CUDA_VERIFY(cudaFreeAsync(one, stream));
 }
@@ -866,9 +578,9 @@ void runFlatTcSearch(
     for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
         const int64_t nq = std::min(kQBatch, nqAll - qb);
         const float* Qb = Q + qb * d;
-        const int64_t qTiles = ceil_div(nq, kTileM);
+        const int64_t qPairs = ceil_div(nq, kPairM);
 
-        auto q16 = res->temp(device, sizeof(__half) * qTiles * kTileM * dpad);
+        auto q16 = res->temp(device, sizeof(__half) * qPairs * kPairM * dpad);
         auto scal = res->temp(device, sizeof(float) * 4); // [absmax, qScale, inv, -]
         auto eps = res->temp(device, sizeof(float) * nq);
         auto thr = res->temp(device, sizeof(float) * nq);
@@ -878,7 +590,7 @@ void runFlatTcSearch(
 
         CUDA_VERIFY(cudaMemsetAsync(scal.data, 0, sizeof(float) * 4, stream));
         CUDA_VERIFY(cudaMemsetAsync(flags.data, 0, sizeof(int) * (nq + 1), stream));
-        CUDA_VERIFY(cudaMemsetAsync(q16.data, 0, sizeof(__half) * qTiles * kTileM * dpad, stream));
+        CUDA_VERIFY(cudaMemsetAsync(q16.data, 0, sizeof(__half) * qPairs * kPairM * dpad, stream));
         float* sc = scal.as<float>();
         runAbsMax(Qb, nq * d, sc + 0, stream);
         tc_query_scale_kernel<<<1, 1, 0, stream>>>(sc + 0, yScale, sc + 1, sc + 2);
@@ -892,7 +604,6 @@ void runFlatTcSearch(
                     baseKey.as<float>(), baseId.as<int>(), cnt);
             CUDA_CHECK_LAST();
         }
-        CUtensorMap mapQ = makeTileMap(q16.as<__half>(), qTiles * kTileM, dpad);
 
         // ---- geometric rounds over the permuted tile order
         struct Round {
@@ -919,7 +630,7 @@ void runFlatTcSearch(
                 int64_t maxS = std::max<int64_t>(1, std::min<int64_t>(512, tiles / 8));
                 for (int64_t S = 1; S <= maxS; S++) {
                     int64_t tps = ceil_div(tiles, S);
-                    int64_t units = qTiles * ceil_div(tiles, tps);
+                    int64_t units = qPairs * ceil_div(tiles, tps);
                     int64_t waves = ceil_div(units, sms);
                     double cost = (double)waves * (double)(tps + 6); // +6: per-unit fixed overhead
                     if (cost < bestCost * 0.999) {
@@ -943,9 +654,9 @@ void runFlatTcSearch(
         }
         size_t arenaBytes = 0, countBytes = 0;
         for (auto& r : rounds) {
-            size_t units = (size_t)qTiles * r.slices;
-            arenaBytes = std::max(arenaBytes, units * 256 * (size_t)r.cap * sizeof(uint2));
-            countBytes = std::max(countBytes, units * 256 * sizeof(int));
+            size_t units = (size_t)qPairs * r.slices;
+            arenaBytes = std::max(arenaBytes, units * kSegsPerUnit * (size_t)r.cap * sizeof(uint2));
+            countBytes = std::max(countBytes, units * kSegsPerUnit * sizeof(int));
         }
         auto arena = res->temp(device, arenaBytes);
         auto counts = res->temp(device, countBytes);
@@ -957,8 +668,10 @@ void runFlatTcSearch(
         for (auto& r : rounds) {
             TcParams p{};
             p.slices = r.slices;
-            p.qTiles = (int)qTiles;
-            p.numUnits = (int)(qTiles * r.slices);
+            p.qPairs = (int)qPairs;
+            p.numUnits = (int)(qPairs * r.slices);
+            p.Q16 = q16.as<__half>();
+            p.accStages = (512 - dpad) / kTileN;
             p.tileBegin = r.begin;
             p.tileEnd = r.end;
             p.tilesPerSlice = r.tilesPerSlice;
@@ -977,7 +690,7 @@ void runFlatTcSearch(
             p.dumpLd = 0;
             p.nq = (int)nq;
             p.debugSkip = getenv("FB200_TC_DEBUG_SKIP") ? atoi(getenv("FB200_TC_DEBUG_SKIP")) : 0;
-            launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+            launchTc<false>(mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
                     k,
