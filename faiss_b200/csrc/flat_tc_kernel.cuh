@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
         if (lane == 0) {
             int ys = 0, bs = 0;
             uint32_t yphase = 0, bphase = 0;
-            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
+            for (int u = blockIdx.x; u < p.numUnits && p.debugSkip < 3; u += gridDim.x) {
                 const int sl = u / p.qPairs;
                 const int pb = p.tileBegin + sl * p.tilesPerSlice;
                 const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
                 ptx::mbar_wait(a_full, it & 1); // both query tiles are in tensor memory
                 ptx::tc_fence_after();
                 for (int pp = pb; pp < pe; pp++) {
-                    ptx::mbar_wait(&y_full[ys], yphase);
+                    if (p.debugSkip < 3)
+                        ptx::mbar_wait(&y_full[ys], yphase);
                     ptx::tc_fence_after();
                     const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
 #pragma unroll 1
                     for (int h = 0; h < 2; h++) {
-                        ptx::mbar_wait(&t_empty[as], aphase ^ 1);
+                        if (p.debugSkip < 4)
+                            ptx::mbar_wait(&t_empty[as], aphase ^ 1);
                         ptx::tc_fence_after();
                         const uint32_t dcol = tmem_base + accBase + (uint32_t)as * kTileN;
                         const uint32_t acol = tmem_base + (uint32_t)(h * colsA);
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
                             aphase ^= 1;
                         }
                     }
-                    ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
+                    if (p.debugSkip < 3)
+                        ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
                     if (++ys == p.yStages) {
                         ys = 0;
                         yphase ^= 1;
@@ -342,10 +345,12 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
             uint32_t ra[32], rb[32];
             ptx::mbar_wait(&t_full[as], aphase);
             ptx::tc_fence_after();
-            ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
+            if (p.debugSkip != 2)
+                ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
             for (int pp = pb; pp < pe; pp++) {
-                ptx::mbar_wait(&b_full[bs], bphase);
-                const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
+                if (p.debugSkip < 3)
+                    ptx::mbar_wait(&b_full[bs], bphase);
+                const int t = p.debugSkip < 3 ? ptx::lds32(ptx::smem_u32(tileS + bs)) : 0;
                 const long long colBase = (long long)t * kTileN + half * 64;
                 const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * 64);
 #pragma unroll
@@ -355,7 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
                     uint2* buf = h ? buf1 : buf0;
                     int& cnt = h ? cnt1 : cnt0;
                     ptx::tmem_ld_wait(); // chunk A landed
-                    ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN + 32), rb);
+                    if (p.debugSkip != 2)
+                        ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN + 32), rb);
                     if (!p.debugSkip)
                         epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
                     ptx::tmem_ld_wait(); // chunk B landed: hand the accumulator stage back to the MMA warp
@@ -370,7 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
                     if (h == 0 || pp + 1 < pe) {
                         ptx::mbar_wait(&t_full[as], aphase);
                         ptx::tc_fence_after();
-                        ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
+                        if (p.debugSkip != 2)
+                            ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
                     }
                     if (!p.debugSkip)
                         epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
