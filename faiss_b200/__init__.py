@@ -552,7 +552,7 @@ def flat_tc_scores_debug(res, Q16, Y16, device=0):
     nq, dpad = Q16.shape
     N = Y16.shape[0]
     res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
-    npad = (N + 127) // 128 * 128
+    npad = (N + 255) // 256 * 256
     S = torch.zeros((nq, npad), dtype=torch.float32, device=Q16.device)
     check(
         lib.b200_flat_tc_scores_debug(

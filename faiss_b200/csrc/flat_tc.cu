@@ -376,11 +376,11 @@ PFN_encodeTiled getEncodeTiled() {
 
 // fp16 matrix [rows][dpad] viewed as (64, rows, dpad/64); one box = (64, 128, dpad/64) = a full
 // K-extent tile laid out [kblock][row][64] with the 128-byte swizzle the UMMA descriptors expect.
-CUtensorMap makeTileMap(const __half* base, int64_t rows, int dpad) {
+CUtensorMap makeTileMap(const __half* base, int64_t rows, int dpad, int boxRows) {
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)kKBlock, (cuuint64_t)rows, (cuuint64_t)(dpad / kKBlock)};
     cuuint64_t strides[2] = {(cuuint64_t)dpad * 2, (cuuint64_t)kKBlock * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)kTileN, (cuuint32_t)(dpad / kKBlock)};
+    cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)boxRows, (cuuint32_t)(dpad / kKBlock)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = getEncodeTiled()(
             &m,
@@ -414,20 +414,21 @@ struct SmemPlan {
 };
 
 SmemPlan planSmem(int KB) {
-    const size_t stage = (size_t)KB * kKBlockBytes;
+    const size_t stage = (size_t)KB * kTileN * kKBlock * 2;
+    const size_t qtiles = (size_t)2 * KB * kTileM * kKBlock * 2;
     const size_t budget = 220 * 1024;
-    const size_t fixed = 1024 /*align slack*/ + 512 /*barriers, tile ids*/ + kBiasSlots * kTileN * 4 /*bias ring*/;
+    const size_t fixed = 1024 /*align slack*/ + 512 /*barriers, tile ids*/ + kBiasSlots * kTileN * 4 /*bias ring*/ + qtiles;
     int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
     FB_THROW_IF_NOT_MSG(ys >= 2, "dimension too large for the tensor-core Flat kernel");
     return {ys, fixed + ys * stage};
 }
 
 template <bool DUMP>
-void launchTc(const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
+void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
     auto kern = flat_tc_kernel<DUMP>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("flat_tc", stream);
-    kern<<<grid, kThreads, smem, stream>>>(my, p);
+    kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
     KernelTiming::end("flat_tc", stream);
     CUDA_CHECK_LAST();
 }
@@ -470,7 +471,7 @@ void runFlatTcPrepareRows(
 
 bool flatTcSupported(int d, int k, int64_t n) {
     int dpad = (int)round_up(d, kKBlock);
-    return dpad <= 256 && k >= 1 && k <= 512 && n >= 32768 && n < (int64_t(1) << 31) - 256;
+    return dpad <= 128 && k >= 1 && k <= 512 && n >= 32768 && n < (int64_t(1) << 31) - 512;
 }
 
 void runFlatTcScoresDebug(
@@ -481,10 +482,10 @@ void runFlatTcScoresDebug(
         int dpad,
         float* S,
         cudaStream_t stream) {
-    FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= 256);
+    FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= 128);
     const int KB = dpad / kKBlock;
     SmemPlan sp = planSmem(KB);
-    CUtensorMap my = makeTileMap(Y16, n, dpad);
+    CUtensorMap my = makeTileMap(Y16, n, dpad, kTileN);
     const int64_t numTiles = ceil_div(n, kTileN);
     const int64_t qPairs = ceil_div(nq, kPairM);
     // the kernel reads whole 256-row query pairs: zero-padded private copy
@@ -504,8 +505,7 @@ void runFlatTcScoresDebug(
     p.slices = 1;
     p.qPairs = (int)qPairs;
     p.numUnits = (int)qPairs;
-    p.Q16 = qpad;
-    p.accStages = (512 - dpad) / kTileN;
+    CUtensorMap mq = makeTileMap(qpad, qPairs * kPairM, dpad, kTileM);
     p.tileBegin = 0;
     p.tileEnd = (int)numTiles;
     p.tilesPerSlice = (int)numTiles;
@@ -526,7 +526,7 @@ void runFlatTcScoresDebug(
     int dev = 0, sms = 0;
     CUDA_VERIFY(cudaGetDevice(&dev));
     CUDA_VERIFY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    launchTc<true>(my, p, (int)std::min<int64_t>(p.numUnits, sms), sp.bytes, stream);
+    launchTc<true>(mq, my, p, (int)std::min<int64_t>(p.numUnits, sms), sp.bytes, stream);
     CUDA_VERIFY(cudaFreeAsync(qpad, stream));
     CUDA_VERIFY(cudaFreeAsync(bias, stream));
     CUDA_VERIFY(cudaFreeAsync(one, stream));
@@ -572,7 +572,7 @@ void runFlatTcSearch(
     const float c1 = 1.01f * (ldexpf(1.f, -10) + (float)dpad * ldexpf(1.f, -22));
     const float c2 = ldexpf(1.f, -22);
 
-    CUtensorMap mapY = makeTileMap(Y16, n, dpad);
+    CUtensorMap mapY = makeTileMap(Y16, n, dpad, kTileN);
 
     const int64_t kQBatch = 16384; // queries per pass (bounds the candidate arena)
     for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
@@ -614,7 +614,7 @@ void runFlatTcSearch(
             int64_t seen = 0;
             while (seen < T) {
                 // schedule knobs (tuning only): first-round tiles, early / late growth factors
-                static const int r0Tiles = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 32;
+                static const int r0Tiles = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 16;
                 static const double gEarly = getenv("FB200_TC_G_EARLY") ? atof(getenv("FB200_TC_G_EARLY")) : 4.0;
                 static const double gLate = getenv("FB200_TC_G_LATE") ? atof(getenv("FB200_TC_G_LATE")) : 4.0;
                 static const int64_t lateFrom = getenv("FB200_TC_LATE_FROM") ? atol(getenv("FB200_TC_LATE_FROM")) : 8192;
@@ -670,8 +670,7 @@ void runFlatTcSearch(
             p.slices = r.slices;
             p.qPairs = (int)qPairs;
             p.numUnits = (int)(qPairs * r.slices);
-            p.Q16 = q16.as<__half>();
-            p.accStages = (512 - dpad) / kTileN;
+            CUtensorMap mapQ = makeTileMap(q16.as<__half>(), qPairs * kPairM, dpad, kTileM);
             p.tileBegin = r.begin;
             p.tileEnd = r.end;
             p.tilesPerSlice = r.tilesPerSlice;
@@ -690,7 +689,7 @@ void runFlatTcSearch(
             p.dumpLd = 0;
             p.nq = (int)nq;
             p.debugSkip = getenv("FB200_TC_DEBUG_SKIP") ? atoi(getenv("FB200_TC_DEBUG_SKIP")) : 0;
-            launchTc<false>(mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+            launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
                     k,

@@ -1,21 +1,25 @@
 // faiss_b200 -- the tcgen05 Flat scoring + filter kernel (included by flat_tc.cu).
 //
+// Shape decisions, each backed by a measurement on B200 (profiles/r01_ubench_tcgen05.txt):
+//   * tcgen05.commit costs MMA throughput: 128x128x16 MMAs with a commit every 8 instructions run
+//     at ~0.95 PFLOP/s, 128x256x16 at ~1.46 (SS) -- so the database tile is N = 256 rows and one
+//     commit pair covers 1024 cycles of tensor work.
+//   * L2 -> SM bandwidth (~8 TB/s chip-wide) caps a one-query-tile CTA at ~1.1 PFLOP/s for d = 128:
+//     a work unit therefore covers TWO query tiles (256 queries); every database tile that lands in
+//     shared memory feeds two MMA groups (accumulators h = 0, 1 -> the two 256-column halves of TMEM).
+//   * tcgen05.ld is not a limit (~770 B/cycle/SM measured), so fp32 accumulators are drained in full.
+//
 // Roles in one persistent CTA (320 threads, one CTA per SM):
-//   warp 0   : TMA producer -- database tiles (128 rows x dpad fp16, 128B-swizzled K-major) through a
-//              multi-stage mbarrier ring, plus a small ring with each tile's bias row and tile id
-//   warp 1   : single-thread tcgen05.mma issuer.  The A operand (queries) lives in TENSOR MEMORY
-//              (TS mode): a work unit covers TWO query tiles (256 queries), so every database tile
-//              that lands in shared memory feeds two MMA groups, and shared memory only serves B.
-//              (SS mode with one query tile needs ~96 KB of smem traffic per 512-cycle tile and
-//              measured ~50% of the MMA floor; profiles/r01_*.)
+//   warp 0   : TMA producer -- the unit's two query tiles once, then database tiles (256 rows x dpad
+//              fp16, 128B-swizzled K-major) through an mbarrier ring, plus a small ring with each
+//              tile's 256 biases and its tile id
+//   warp 1   : single-thread tcgen05.mma issuer (SS mode, M=128 N=256 K=16, fp32 accumulate in TMEM)
 //   warps 2-9: epilogue.  A thread owns one TMEM lane = one query row of each of the unit's two query
-//              tiles, and 64 of a tile's 128 columns.  It streams accumulators with tcgen05.ld in
+//              tiles, and 128 of a tile's 256 columns.  It streams accumulators with tcgen05.ld in
 //              32-column chunks (software-pipelined against the filter), computes
-//              score = acc * inv + bias with FFMA2, folds the chunk with FMNMX3 and compares one
-//              maximum per 8 columns against the query's threshold.  Survivors (rare) are appended
-//              with plain stores to a thread-private candidate segment.
-//   TMEM map : [0, dpad) columns = the two A tiles (dpad/2 columns each, fp16 pairs per column),
-//              then (512 - dpad)/128 accumulator stages of 128 columns.
+//              score = acc * inv + bias with FFMA2, folds 8 columns with FMNMX3 and compares against the
+//              query's threshold held in a register.  Survivors (rare) are appended with plain stores
+//              to a thread-private candidate segment; scores never reach HBM.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -28,15 +32,14 @@ namespace tc {
 
 constexpr int kTileM = 128;       // queries per MMA tile (TMEM lanes)
 constexpr int kPairM = 256;       // queries per work unit (two MMA tiles)
-constexpr int kTileN = 128;       // database rows per tile (TMEM columns per accumulator stage)
+constexpr int kTileN = 256;       // database rows per tile (TMEM columns per accumulator)
 constexpr int kKBlock = 64;       // fp16 elements per 128-byte swizzle row
-constexpr int kKBlockBytes = kTileN * kKBlock * 2; // 16 KiB per (128 rows x 64 halfs)
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kMaxYStages = 6;
-constexpr int kMaxAccStages = 4;
-constexpr int kBiasSlots = 8;
+constexpr int kBiasSlots = 4;
 constexpr int kSegsPerUnit = 512; // 256 query rows x 2 column halves
+constexpr int kColsPerThread = kTileN / 2; // columns of a tile one epilogue thread filters
 
 struct TcParams {
     int numUnits;
@@ -48,10 +51,8 @@ struct TcParams {
     unsigned long long permA, permB, numTiles;
     int KB;             // dpad / 64
     int yStages;
-    int accStages;      // (512 - dpad) / 128
-    const __half* Q16;  // [qPairs*256][dpad] scaled fp16 queries, zero padded
     const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
-    const float* bias;  // [numTiles*128], -inf padded
+    const float* bias;  // [numTiles*256], -inf padded
     const float* thr;   // [nq]  pass if score > thr
     uint2* cand;        // [numUnits*512][cap] (score bits, row)
     int cap;
@@ -64,42 +65,6 @@ struct TcParams {
 
 __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
     return (int)(((unsigned long long)pos * p.permA + p.permB) % p.numTiles);
-}
-
-// D[tmem] (+)= A[tmem] * B[smem desc]^T   (TS mode)
-__device__ __forceinline__ void mma_f16_ts(
-        uint32_t tmem_d,
-        uint32_t tmem_a,
-        uint64_t desc_b,
-        uint32_t idesc,
-        uint32_t accumulate) {
-    asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "setp.ne.b32 p, %4, 0;\n"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-            "}\n" ::"r"(tmem_d),
-            "r"(tmem_a),
-            "l"(desc_b),
-            "r"(idesc),
-            "r"(accumulate)
-            : "memory");
-}
-
-// 32 lanes x 32 columns registers -> TMEM
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-            "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-            "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-            "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-            "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-            : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // Filter 32 columns of one query row: score = acc * inv + bias; one maximum per 8 columns against the
@@ -158,40 +123,44 @@ __device__ __forceinline__ void epi_filter32(
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_constant__ CUtensorMap mapY, const TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
+        const __grid_constant__ CUtensorMap mapQ,
+        const __grid_constant__ CUtensorMap mapY,
+        const TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms need it)
     unsigned char* smem = reinterpret_cast<unsigned char*>(
             (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    const int stageBytes = p.KB * kKBlockBytes;
-    unsigned char* sY = smem;
+    const int qBytes = p.KB * kTileM * kKBlock * 2;     // one query tile   (128 rows)
+    const int stageBytes = p.KB * kTileN * kKBlock * 2; // one database tile (256 rows)
+    unsigned char* sQ = smem;                            // two query tiles
+    unsigned char* sY = smem + 2 * qBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sY + (size_t)p.yStages * stageBytes);
-    uint64_t* a_full = bars + 0;
-    uint64_t* a_empty = bars + 1;
+    uint64_t* q_full = bars + 0;
+    uint64_t* q_empty = bars + 1;
     uint64_t* y_full = bars + 2;
     uint64_t* y_empty = y_full + kMaxYStages;
-    uint64_t* t_full = y_empty + kMaxYStages;
-    uint64_t* t_empty = t_full + kMaxAccStages;
-    uint64_t* b_full = t_empty + kMaxAccStages;
+    uint64_t* t_full = y_empty + kMaxYStages; // [2] one per accumulator half
+    uint64_t* t_empty = t_full + 2;
+    uint64_t* b_full = t_empty + 2;
     uint64_t* b_empty = b_full + kBiasSlots;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kBiasSlots);
     int* tileS = reinterpret_cast<int*>(tmem_slot + 2);                // [kBiasSlots]
-    float* biasS = reinterpret_cast<float*>(tileS + kBiasSlots + 2);   // [kBiasSlots][128], 16B aligned
+    float* biasS = reinterpret_cast<float*>(tileS + kBiasSlots + 2);   // [kBiasSlots][256], 16B aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int colsA = p.KB * 32;            // TMEM columns per A tile
-    const uint32_t accBase = 2 * colsA;     // first accumulator column
 
     if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&mapQ);
         ptx::prefetch_tensormap(&mapY);
-        ptx::mbar_init(a_full, kEpiWarps);
-        ptx::mbar_init(a_empty, 1);
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(q_empty, 1);
         for (int i = 0; i < p.yStages; i++) {
             ptx::mbar_init(&y_full[i], 1);
             ptx::mbar_init(&y_empty[i], 1);
         }
-        for (int i = 0; i < p.accStages; i++) {
+        for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&t_full[i], 1);
             ptx::mbar_init(&t_empty[i], kEpiWarps);
         }
@@ -214,8 +183,14 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
         if (lane == 0) {
             int ys = 0, bs = 0;
             uint32_t yphase = 0, bphase = 0;
-            for (int u = blockIdx.x; u < p.numUnits && p.debugSkip < 3; u += gridDim.x) {
+            int it = 0;
+            for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
+                const int pair = u % p.qPairs;
                 const int sl = u / p.qPairs;
+                ptx::mbar_wait(q_empty, (it & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(q_full, (uint32_t)(2 * qBytes));
+                ptx::tma_load_3d(sQ, &mapQ, q_full, 0, pair * kPairM, 0);
+                ptx::tma_load_3d(sQ + qBytes, &mapQ, q_full, 0, pair * kPairM + kTileM, 0);
                 const int pb = p.tileBegin + sl * p.tilesPerSlice;
                 const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
                 for (int pp = pb; pp < pe; pp++) {
@@ -243,91 +218,63 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
         // ================================ MMA issuer ================================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN);
-            int ys = 0, as = 0;
-            uint32_t yphase = 0, aphase = 0;
+            int ys = 0;
+            uint32_t yphase = 0, tphase = 0;
             int it = 0;
+            const uint32_t sQaddr = ptx::smem_u32(sQ);
             const uint32_t sYaddr = ptx::smem_u32(sY);
+            const int qkb = kTileM * kKBlock * 2; // bytes per K-block of a query tile
+            const int ykb = kTileN * kKBlock * 2; // bytes per K-block of a database tile
             for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
                 const int sl = u / p.qPairs;
                 const int pb = p.tileBegin + sl * p.tilesPerSlice;
                 const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
-                ptx::mbar_wait(a_full, it & 1); // both query tiles are in tensor memory
+                ptx::mbar_wait(q_full, it & 1);
                 ptx::tc_fence_after();
                 for (int pp = pb; pp < pe; pp++) {
-                    if (p.debugSkip < 3)
-                        ptx::mbar_wait(&y_full[ys], yphase);
+                    ptx::mbar_wait(&y_full[ys], yphase);
                     ptx::tc_fence_after();
                     const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
 #pragma unroll 1
                     for (int h = 0; h < 2; h++) {
-                        if (p.debugSkip < 4)
-                            ptx::mbar_wait(&t_empty[as], aphase ^ 1);
+                        ptx::mbar_wait(&t_empty[h], tphase ^ 1); // epilogue drained this accumulator
                         ptx::tc_fence_after();
-                        const uint32_t dcol = tmem_base + accBase + (uint32_t)as * kTileN;
-                        const uint32_t acol = tmem_base + (uint32_t)(h * colsA);
+                        const uint32_t dcol = tmem_base + (uint32_t)h * kTileN;
+                        const uint32_t qaddr = sQaddr + (uint32_t)h * (uint32_t)qBytes;
                         for (int kb = 0; kb < p.KB; kb++) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; k4++) {
-                                uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * kKBlockBytes + k4 * 32);
-                                mma_f16_ts(dcol, acol + kb * 32 + k4 * 8, db, idesc, (kb | k4) != 0 ? 1u : 0u);
+                                uint64_t da = ptx::make_smem_desc_sw128(qaddr + kb * qkb + k4 * 32);
+                                uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * ykb + k4 * 32);
+                                ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
                             }
                         }
-                        ptx::mma_commit(&t_full[as]); // accumulator stage ready for the epilogue
-                        if (++as == p.accStages) {
-                            as = 0;
-                            aphase ^= 1;
-                        }
+                        ptx::mma_commit(&t_full[h]); // accumulator ready for the epilogue
                     }
-                    if (p.debugSkip < 3)
-                        ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
+                    ptx::mma_commit(&y_empty[ys]); // smem stage reusable once these MMAs retire
+                    tphase ^= 1;
                     if (++ys == p.yStages) {
                         ys = 0;
                         yphase ^= 1;
                     }
                 }
-                ptx::mma_commit(a_empty); // the A tiles may be overwritten
+                ptx::mma_commit(q_empty); // the query tiles may be overwritten
             }
         }
     } else {
         // ================================ epilogue ================================
         const int ew = warp - 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // which 64 columns of a tile; also which A tile this warp loads
+        const int half = ew >> 2;      // which 128 columns of a tile
         const int row = quarter * 32 + lane;
         const float inv = *p.invScalePtr;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t lane_acc = lane_base + accBase + (uint32_t)(half * 64);
-        int as = 0, bs = 0;
-        uint32_t aphase = 0, bphase = 0;
-        int it = 0;
-        for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
+        const uint32_t lane_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerThread);
+        int bs = 0;
+        uint32_t bphase = 0, tphase = 0;
+        for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
             const int pair = u % p.qPairs;
             const int sl = u / p.qPairs;
-            // ---- load this warp's share of the A operand into tensor memory
-            {
-                ptx::mbar_wait(a_empty, (it & 1) ^ 1); // previous unit's MMAs have retired
-                ptx::tc_fence_after();
-                const long long qa = (long long)pair * kPairM + half * kTileM + row;
-                const uint4* src = reinterpret_cast<const uint4*>(p.Q16 + qa * (p.KB * kKBlock));
-                for (int kb = 0; kb < p.KB; kb++) {
-                    uint32_t w[32];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint4 v = __ldg(src + kb * 8 + j);
-                        w[4 * j + 0] = v.x;
-                        w[4 * j + 1] = v.y;
-                        w[4 * j + 2] = v.z;
-                        w[4 * j + 3] = v.w;
-                    }
-                    tmem_st_32x32b_x32(lane_base + (uint32_t)(half * colsA + kb * 32), w);
-                }
-                tmem_st_wait();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(a_full);
-            }
-            // ---- per-thread filter state for its two queries (one per query tile of the pair)
+            // per-thread filter state for its two queries (one per query tile of the pair)
             const int q0 = pair * kPairM + row;
             const int q1 = q0 + kTileM;
             const float thr0 = (!DUMP && q0 < p.nq) ? p.thr[q0] : CUDART_INF_F;
@@ -340,48 +287,51 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(const __grid_const
             const int pb = p.tileBegin + sl * p.tilesPerSlice;
             const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
 
-            // Software pipeline at 32-column granularity: while chunk A (columns 0..31 of this warp's
-            // half) is filtered, the TMEM load of chunk B is in flight, and vice versa across stages.
+            // Chunk stream per database tile: (h=0: c0..c3), (h=1: c0..c3), 32 columns each.  While one
+            // chunk is filtered the TMEM load of the next is in flight (two register sets).
             uint32_t ra[32], rb[32];
-            ptx::mbar_wait(&t_full[as], aphase);
+            ptx::mbar_wait(&t_full[0], tphase);
             ptx::tc_fence_after();
-            if (p.debugSkip != 2)
-                ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
+            ptx::tmem_ld_32x32b_x32(lane_acc, ra);
             for (int pp = pb; pp < pe; pp++) {
-                if (p.debugSkip < 3)
-                    ptx::mbar_wait(&b_full[bs], bphase);
-                const int t = p.debugSkip < 3 ? ptx::lds32(ptx::smem_u32(tileS + bs)) : 0;
-                const long long colBase = (long long)t * kTileN + half * 64;
-                const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * 64);
+                ptx::mbar_wait(&b_full[bs], bphase);
+                const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
+                const long long colBase = (long long)t * kTileN + half * kColsPerThread;
+                const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * kColsPerThread);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
+                for (int ci = 0; ci < 8; ci++) {
+                    const int h = ci >> 2, c = ci & 3;
                     const int q = h ? q1 : q0;
                     const float thr = h ? thr1 : thr0;
                     uint2* buf = h ? buf1 : buf0;
                     int& cnt = h ? cnt1 : cnt0;
-                    ptx::tmem_ld_wait(); // chunk A landed
-                    if (p.debugSkip != 2)
-                        ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN + 32), rb);
-                    if (!p.debugSkip)
-                        epi_filter32<DUMP>(p, ra, q, colBase, inv, thr, bp, buf, cnt);
-                    ptx::tmem_ld_wait(); // chunk B landed: hand the accumulator stage back to the MMA warp
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0)
-                        ptx::mbar_arrive(&t_empty[as]);
-                    if (++as == p.accStages) {
-                        as = 0;
-                        aphase ^= 1;
+                    uint32_t(&cur)[32] = (ci & 1) ? rb : ra;
+                    uint32_t(&nxt)[32] = (ci & 1) ? ra : rb;
+                    ptx::tmem_ld_wait(); // chunk ci is in registers
+                    if (c == 3) {
+                        // all four chunks of accumulator h are out of TMEM: hand it back to the MMA warp
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0)
+                            ptx::mbar_arrive(&t_empty[h]);
                     }
-                    if (h == 0 || pp + 1 < pe) {
-                        ptx::mbar_wait(&t_full[as], aphase);
+                    // prefetch the next chunk
+                    if (ci < 7) {
+                        if (c == 3) { // first chunk of accumulator 1 of this tile
+                            ptx::mbar_wait(&t_full[1], tphase);
+                            ptx::tc_fence_after();
+                        }
+                        ptx::tmem_ld_32x32b_x32(
+                                lane_acc + (uint32_t)((ci + 1) >> 2) * kTileN + (uint32_t)(((ci + 1) & 3) * 32), nxt);
+                    } else if (pp + 1 < pe) { // first chunk of the next tile
+                        ptx::mbar_wait(&t_full[0], tphase ^ 1);
                         ptx::tc_fence_after();
-                        if (p.debugSkip != 2)
-                            ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)(as * kTileN), ra);
+                        ptx::tmem_ld_32x32b_x32(lane_acc, nxt);
                     }
                     if (!p.debugSkip)
-                        epi_filter32<DUMP>(p, rb, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
+                        epi_filter32<DUMP>(p, cur, q, colBase + c * 32, inv, thr, bp + c * 128, buf, cnt);
                 }
+                tphase ^= 1;
                 __syncwarp();
                 if (lane == 0)
                     ptx::mbar_arrive(&b_empty[bs]);

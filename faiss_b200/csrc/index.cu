@@ -330,7 +330,7 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
         return;
     auto stream = stream_();
     const idx_t n = this->ntotal;
-    const int64_t padRows = round_up(n, 128) + 128;
+    const int64_t padRows = round_up(n, 256) + 256; // whole 256-row tiles, -inf beyond n
     y16_.resize((size_t)n * dpad_, stream);
     bias_.resize((size_t)padRows, stream);
     auto scal = resources_->temp(config_.device, sizeof(float) * 2);
