@@ -298,38 +298,49 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                 const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
                 const long long colBase = (long long)t * kTileN + half * kColsPerThread;
                 const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * kColsPerThread);
-#pragma unroll
-                for (int ci = 0; ci < 8; ci++) {
-                    const int h = ci >> 2, c = ci & 3;
+                // (kept as a rolled loop over the two accumulators and two chunk pairs: the filter body
+                // is large, and unrolling all eight chunks overflows the instruction cache)
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
                     const int q = h ? q1 : q0;
                     const float thr = h ? thr1 : thr0;
                     uint2* buf = h ? buf1 : buf0;
-                    int& cnt = h ? cnt1 : cnt0;
-                    uint32_t(&cur)[32] = (ci & 1) ? rb : ra;
-                    uint32_t(&nxt)[32] = (ci & 1) ? ra : rb;
-                    ptx::tmem_ld_wait(); // chunk ci is in registers
-                    if (c == 3) {
-                        // all four chunks of accumulator h are out of TMEM: hand it back to the MMA warp
-                        ptx::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0)
-                            ptx::mbar_arrive(&t_empty[h]);
-                    }
-                    // prefetch the next chunk
-                    if (ci < 7) {
-                        if (c == 3) { // first chunk of accumulator 1 of this tile
+                    int cnt = h ? cnt1 : cnt0;
+                    const uint32_t acc = lane_acc + (uint32_t)h * kTileN;
+#pragma unroll 1
+                    for (int cp = 0; cp < 2; cp++) {
+                        const int c0 = 2 * cp;
+                        ptx::tmem_ld_wait(); // chunk c0 (in ra) has landed
+                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)((c0 + 1) * 32), rb);
+                        if (!p.debugSkip)
+                            epi_filter32<DUMP>(p, ra, q, colBase + c0 * 32, inv, thr, bp + c0 * 128, buf, cnt);
+                        ptx::tmem_ld_wait(); // chunk c0+1 (in rb) has landed
+                        if (cp == 1) {
+                            // all four chunks of accumulator h are out of TMEM: hand it back to the MMA warp
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0)
+                                ptx::mbar_arrive(&t_empty[h]);
+                        }
+                        // prefetch the next chunk into ra
+                        if (cp == 0) {
+                            ptx::tmem_ld_32x32b_x32(acc + 64u, ra);
+                        } else if (h == 0) { // first chunk of accumulator 1 of this tile
                             ptx::mbar_wait(&t_full[1], tphase);
                             ptx::tc_fence_after();
+                            ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)kTileN, ra);
+                        } else if (pp + 1 < pe) { // first chunk of the next tile
+                            ptx::mbar_wait(&t_full[0], tphase ^ 1);
+                            ptx::tc_fence_after();
+                            ptx::tmem_ld_32x32b_x32(lane_acc, ra);
                         }
-                        ptx::tmem_ld_32x32b_x32(
-                                lane_acc + (uint32_t)((ci + 1) >> 2) * kTileN + (uint32_t)(((ci + 1) & 3) * 32), nxt);
-                    } else if (pp + 1 < pe) { // first chunk of the next tile
-                        ptx::mbar_wait(&t_full[0], tphase ^ 1);
-                        ptx::tc_fence_after();
-                        ptx::tmem_ld_32x32b_x32(lane_acc, nxt);
+                        if (!p.debugSkip)
+                            epi_filter32<DUMP>(p, rb, q, colBase + (c0 + 1) * 32, inv, thr, bp + (c0 + 1) * 128, buf, cnt);
                     }
-                    if (!p.debugSkip)
-                        epi_filter32<DUMP>(p, cur, q, colBase + c * 32, inv, thr, bp + c * 128, buf, cnt);
+                    if (h)
+                        cnt1 = cnt;
+                    else
+                        cnt0 = cnt;
                 }
                 tphase ^= 1;
                 __syncwarp();
