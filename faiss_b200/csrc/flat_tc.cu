@@ -425,7 +425,9 @@ SmemPlan planSmem(int KB) {
 
 template <bool DUMP>
 void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto kern = flat_tc_kernel<DUMP>;
+    // FB200_TC_DEBUG_SKIP=1 (timing experiments only): skip the filter, keep the TMEM loads
+    static const bool dbg = getenv("FB200_TC_DEBUG_SKIP") && atoi(getenv("FB200_TC_DEBUG_SKIP")) != 0;
+    auto kern = dbg ? flat_tc_kernel<DUMP, 1> : flat_tc_kernel<DUMP, 0>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("flat_tc", stream);
     kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
@@ -661,7 +663,7 @@ void runFlatTcSearch(
         auto arena = res->temp(device, arenaBytes);
         auto counts = res->temp(device, countBytes);
 
-        const int selWarps = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / SmemTopK<int>::bytes(LIST, 64)));
+        const int selWarps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / SmemTopK<int>::bytes(LIST, 64)));
         const size_t selSmem = SmemTopK<int>::bytes(LIST, 64) * selWarps;
         CUDA_VERIFY(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)selSmem));
 
@@ -688,7 +690,6 @@ void runFlatTcSearch(
             p.dump = nullptr;
             p.dumpLd = 0;
             p.nq = (int)nq;
-            p.debugSkip = getenv("FB200_TC_DEBUG_SKIP") ? atoi(getenv("FB200_TC_DEBUG_SKIP")) : 0;
             launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
@@ -708,7 +709,7 @@ void runFlatTcSearch(
 
         // ---- exact re-rank
         {
-            const int rrWarps = (int)std::max<size_t>(1, std::min<size_t>(4, (96 * 1024) / SmemTopK<int>::bytes(KL, 64)));
+            const int rrWarps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / SmemTopK<int>::bytes(KL, 64)));
             const size_t rrSmem = SmemTopK<int>::bytes(KL, 64) * rrWarps;
             float* oD = outD + qb * k;
             idx_t* oI = outI + qb * k;

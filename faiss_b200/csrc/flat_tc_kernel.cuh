@@ -60,7 +60,6 @@ struct TcParams {
     float* dump;        // debug: raw accumulators [nq][dumpLd]
     long long dumpLd;
     int nq;
-    int debugSkip;      // timing experiments only: 1 = skip the filter (TMEM loads still issued)
 };
 
 __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
@@ -122,7 +121,70 @@ __device__ __forceinline__ void epi_filter32(
     }
 }
 
+// 64 columns at once (two 32-column register sets): twice the independent work per warp, which the
+// two-warps-per-scheduler epilogue needs to cover its fixed-latency dependency stalls.
 template <bool DUMP>
+__device__ __forceinline__ void epi_filter64(
+        const TcParams& p,
+        const uint32_t (&r0)[32],
+        const uint32_t (&r1)[32],
+        int q,
+        long long colBase,
+        float inv,
+        float thr,
+        uint32_t bp,
+        uint2* buf,
+        int& cnt) {
+    if (DUMP) {
+        epi_filter32<true>(p, r0, q, colBase, inv, thr, bp, buf, cnt);
+        epi_filter32<true>(p, r1, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
+        return;
+    }
+    float v[64];
+    float mg[8];
+    // two independent 8-column groups per step (one from each register set), biases loaded just in time
+#pragma unroll
+    for (int gg = 0; gg < 4; gg++) {
+        const float4 x0 = ptx::lds128(bp + (2 * gg) * 16);
+        const float4 x1 = ptx::lds128(bp + (2 * gg + 1) * 16);
+        const float4 y0 = ptx::lds128(bp + 128 + (2 * gg) * 16);
+        const float4 y1 = ptx::lds128(bp + 128 + (2 * gg + 1) * 16);
+        const int o = 8 * gg;
+        ptx::fma2(v[o + 0], v[o + 1], __uint_as_float(r0[o + 0]), __uint_as_float(r0[o + 1]), inv, x0.x, x0.y);
+        ptx::fma2(v[32 + o + 0], v[32 + o + 1], __uint_as_float(r1[o + 0]), __uint_as_float(r1[o + 1]), inv, y0.x, y0.y);
+        ptx::fma2(v[o + 2], v[o + 3], __uint_as_float(r0[o + 2]), __uint_as_float(r0[o + 3]), inv, x0.z, x0.w);
+        ptx::fma2(v[32 + o + 2], v[32 + o + 3], __uint_as_float(r1[o + 2]), __uint_as_float(r1[o + 3]), inv, y0.z, y0.w);
+        ptx::fma2(v[o + 4], v[o + 5], __uint_as_float(r0[o + 4]), __uint_as_float(r0[o + 5]), inv, x1.x, x1.y);
+        ptx::fma2(v[32 + o + 4], v[32 + o + 5], __uint_as_float(r1[o + 4]), __uint_as_float(r1[o + 5]), inv, y1.x, y1.y);
+        ptx::fma2(v[o + 6], v[o + 7], __uint_as_float(r0[o + 6]), __uint_as_float(r0[o + 7]), inv, x1.z, x1.w);
+        ptx::fma2(v[32 + o + 6], v[32 + o + 7], __uint_as_float(r1[o + 6]), __uint_as_float(r1[o + 7]), inv, y1.z, y1.w);
+        const float a = ptx::max3(v[o + 0], v[o + 1], v[o + 2]);
+        const float e = ptx::max3(v[32 + o + 0], v[32 + o + 1], v[32 + o + 2]);
+        const float c = ptx::max3(v[o + 3], v[o + 4], v[o + 5]);
+        const float f = ptx::max3(v[32 + o + 3], v[32 + o + 4], v[32 + o + 5]);
+        mg[gg] = ptx::max3(a, c, fmaxf(v[o + 6], v[o + 7]));
+        mg[4 + gg] = ptx::max3(e, f, fmaxf(v[32 + o + 6], v[32 + o + 7]));
+    }
+    const float m = fmaxf(ptx::max3(mg[0], mg[1], mg[2]), fmaxf(ptx::max3(mg[3], mg[4], mg[5]), fmaxf(mg[6], mg[7])));
+    if (m > thr) {
+        const unsigned rowBase = (unsigned)colBase;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            if (mg[g] > thr) {
+#pragma unroll
+                for (int j = 8 * g; j < 8 * g + 8; j++) {
+                    if (v[j] > thr) {
+                        if (cnt < p.cap)
+                            buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
+                        cnt++;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool DUMP, int DBG>
 __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
         const __grid_constant__ CUtensorMap mapQ,
         const __grid_constant__ CUtensorMap mapY,
@@ -287,19 +349,14 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             const int pb = p.tileBegin + sl * p.tilesPerSlice;
             const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
 
-            // Chunk stream per database tile: (h=0: c0..c3), (h=1: c0..c3), 32 columns each.  While one
-            // chunk is filtered the TMEM load of the next is in flight (two register sets).
-            uint32_t ra[32], rb[32];
-            ptx::mbar_wait(&t_full[0], tphase);
-            ptx::tc_fence_after();
-            ptx::tmem_ld_32x32b_x32(lane_acc, ra);
+            // Block stream per database tile: (h=0: blocks 0,1), (h=1: blocks 0,1), 64 columns each
+            // (two x32 TMEM loads), filtered together for instruction-level parallelism.
+            uint32_t a0[32], a1[32];
             for (int pp = pb; pp < pe; pp++) {
                 ptx::mbar_wait(&b_full[bs], bphase);
                 const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
                 const long long colBase = (long long)t * kTileN + half * kColsPerThread;
                 const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * kColsPerThread);
-                // (kept as a rolled loop over the two accumulators and two chunk pairs: the filter body
-                // is large, and unrolling all eight chunks overflows the instruction cache)
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const int q = h ? q1 : q0;
@@ -307,35 +364,21 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     uint2* buf = h ? buf1 : buf0;
                     int cnt = h ? cnt1 : cnt0;
                     const uint32_t acc = lane_acc + (uint32_t)h * kTileN;
+                    ptx::mbar_wait(&t_full[h], tphase);
+                    ptx::tc_fence_after();
 #pragma unroll 1
-                    for (int cp = 0; cp < 2; cp++) {
-                        const int c0 = 2 * cp;
-                        ptx::tmem_ld_wait(); // chunk c0 (in ra) has landed
-                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)((c0 + 1) * 32), rb);
-                        if (!p.debugSkip)
-                            epi_filter32<DUMP>(p, ra, q, colBase + c0 * 32, inv, thr, bp + c0 * 128, buf, cnt);
-                        ptx::tmem_ld_wait(); // chunk c0+1 (in rb) has landed
-                        if (cp == 1) {
-                            // all four chunks of accumulator h are out of TMEM: hand it back to the MMA warp
+                    for (int blk = 0; blk < 2; blk++) {
+                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64), a0);
+                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64 + 32), a1);
+                        ptx::tmem_ld_wait();
+                        if (blk == 1) { // the accumulator is out of TMEM: hand it back to the MMA warp
                             ptx::tc_fence_before();
                             __syncwarp();
                             if (lane == 0)
                                 ptx::mbar_arrive(&t_empty[h]);
                         }
-                        // prefetch the next chunk into ra
-                        if (cp == 0) {
-                            ptx::tmem_ld_32x32b_x32(acc + 64u, ra);
-                        } else if (h == 0) { // first chunk of accumulator 1 of this tile
-                            ptx::mbar_wait(&t_full[1], tphase);
-                            ptx::tc_fence_after();
-                            ptx::tmem_ld_32x32b_x32(lane_acc + (uint32_t)kTileN, ra);
-                        } else if (pp + 1 < pe) { // first chunk of the next tile
-                            ptx::mbar_wait(&t_full[0], tphase ^ 1);
-                            ptx::tc_fence_after();
-                            ptx::tmem_ld_32x32b_x32(lane_acc, ra);
-                        }
-                        if (!p.debugSkip)
-                            epi_filter32<DUMP>(p, rb, q, colBase + (c0 + 1) * 32, inv, thr, bp + (c0 + 1) * 128, buf, cnt);
+                        if (DBG == 0)
+                            epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, bp + blk * 256, buf, cnt);
                     }
                     if (h)
                         cnt1 = cnt;
