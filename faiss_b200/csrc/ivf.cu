@@ -424,6 +424,7 @@ void runIvfFlatScan(
         auto partD = res->temp(device, sizeof(float) * nb * nprobe * k);
         auto partI = res->temp(device, sizeof(idx_t) * nb * nprobe * k);
         dim3 grid((unsigned)nprobe, (unsigned)nb);
+        KernelTiming::begin("ivfflat_scan", stream);
         if (metric == METRIC_L2) {
             CUDA_VERIFY(cudaFuncSetAttribute(
                     ivfflat_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -437,6 +438,7 @@ void runIvfFlatScan(
                     Q + q0 * d, d, probes + q0 * nprobe, nprobe, listStart, listLen, arenaVecs, arenaIds, k, LIST,
                     partD.as<float>(), partI.as<idx_t>());
         }
+        KernelTiming::end("ivfflat_scan", stream);
         CUDA_CHECK_LAST();
         runMergeTopKKeyspace(
                 partD.as<float>(), partI.as<idx_t>(), nb, nprobe, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
@@ -577,6 +579,7 @@ void runIvfPqScan(
         auto partD = res->temp(device, sizeof(float) * nb * nprobe * k);
         auto partI = res->temp(device, sizeof(idx_t) * nb * nprobe * k);
         dim3 grid((unsigned)nprobe, (unsigned)nb);
+        KernelTiming::begin("ivfpq_scan", stream);
         if (metric == METRIC_L2) {
             CUDA_VERIFY(cudaFuncSetAttribute(
                     ivfpq_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -590,6 +593,7 @@ void runIvfPqScan(
                     Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, coarseCentroids, pqCentroids,
                     M, ksub, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(), partI.as<idx_t>());
         }
+        KernelTiming::end("ivfpq_scan", stream);
         CUDA_CHECK_LAST();
         runMergeTopKKeyspace(
                 partD.as<float>(), partI.as<idx_t>(), nb, nprobe, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
