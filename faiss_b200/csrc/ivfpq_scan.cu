@@ -186,33 +186,43 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
     const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
     const unsigned lane4 = (unsigned)lane << 2;
     const int ngroups = (len + 31) >> 5;
-    for (int g = warp; g < ngroups; g += kWarps) {
-        const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-        uint4 c4[M / 16];
+    // kU groups per iteration: all of a lane's 128-bit loads are issued before the first lookup, so each
+    // warp keeps kU * M/16 * 512 B in flight (memory-level parallelism for the HBM stream)
+    constexpr int kU = 4;
+    for (int g0 = warp * kU; g0 < ngroups; g0 += kWarps * kU) {
+        uint4 c4[kU][M / 16];
 #pragma unroll
-        for (int h = 0; h < M / 16; h++)
-            c4[h] = __ldg(gp + h * 32);
-        float a0 = 0.f, a1 = 0.f;
+        for (int u = 0; u < kU; u++) {
+            const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
+            const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
 #pragma unroll
-        for (int h = 0; h < M / 16; h++) {
-            const unsigned wds[4] = {c4[h].x, c4[h].y, c4[h].z, c4[h].w};
+            for (int h = 0; h < M / 16; h++)
+                c4[u][h] = __ldg(gp + h * 32);
+        }
 #pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
+        for (int u = 0; u < kU; u++) {
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int j = h * 16 + wi * 4 + b;
-                    // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
-                    const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
-                    const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
-                    if (j & 1)
-                        a1 += val;
-                    else
-                        a0 += val;
+            for (int h = 0; h < M / 16; h++) {
+                const unsigned wds[4] = {c4[u][h].x, c4[u][h].y, c4[u][h].z, c4[u][h].w};
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int j = h * 16 + wi * 4 + b;
+                        // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
+                        const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
+                        const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
+                        if (j & 1)
+                            a1 += val;
+                        else
+                            a0 += val;
+                    }
                 }
             }
+            const int v = (g0 + u) * 32 + lane;
+            w.add(g0 + u < ngroups && v < len, a0 + a1, v);
         }
-        const int v = g * 32 + lane;
-        w.add(v < len, a0 + a1, v);
     }
     const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
     merge_and_write(w, warp, lists, perWarp, LIST, k, arenaIds + listStart[l], add, oD, oI);
