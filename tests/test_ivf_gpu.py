@@ -75,11 +75,12 @@ def test_ivfpq_add_reproduces_reference_lists(res, golden):
 
 
 @pytest.mark.parametrize("metric", [1, 0])
-def test_ivfflat_vs_oracle_and_preassigned(res, metric):
+@pytest.mark.parametrize("d", [40, 128, 256])
+def test_ivfflat_vs_oracle_and_preassigned(res, metric, d):
     import faiss_b200 as fb
 
     rs = np.random.RandomState(3)
-    N, d, nlist, nq, k = 20000, 40, 50, 60, 20
+    N, nlist, nq, k = 20000, 50, 60, 20
     xb = rs.rand(N, d).astype(np.float32)
     xq = rs.rand(nq, d).astype(np.float32)
     idx = fb.GpuIndexIVFFlat(res, d, nlist, metric)
