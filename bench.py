@@ -127,10 +127,18 @@ def gen_queries(torch, device, nq, d):
 
 
 def host_threads():
+    """CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
 
 
 def cpu_reference_qps(xb_host, xq_host, k, budget_s, steps=1, warmup=0):
@@ -141,6 +149,25 @@ def cpu_reference_qps(xb_host, xq_host, k, budget_s, steps=1, warmup=0):
     cores = host_threads()
     if ref.available():
         ref.set_omp_threads(cores)
+        ref.set_blas_threads(cores)
+        # Bound the work: the reference's brute-force search is linear in the number of database rows,
+        # so when 1000 queries over all N rows would blow the time budget (it does on a 16-CPU cgroup
+        # quota with this image's pthreads OpenBLAS), time a leading slice of the rows and scale.
+        nfull = xb_host.shape[0]
+        probe_rows = min(nfull, 250_000)
+        pidx = ref.IndexFlat(xb_host.shape[1], 1)
+        pidx.add(xb_host[:probe_rows])
+        nsp = int(min(xq_host.shape[0], max(1000, 128000 // xb_host.shape[1] + 1)))
+        t0 = time.time()
+        pidx.search(xq_host[:nsp], k)
+        t_probe = time.time() - t0
+        del pidx
+        per_step_budget = max(10.0, budget_s / max(2, steps + warmup))
+        frac = 1.0
+        while frac > 1.0 / 64 and t_probe * (nfull * frac / probe_rows) > per_step_budget:
+            frac /= 2
+        nrows = int(nfull * frac)
+        xb_host = xb_host[:nrows]
         idx = ref.IndexFlat(xb_host.shape[1], 1)
         t0 = time.time()
         idx.add(xb_host)
@@ -162,9 +189,10 @@ def cpu_reference_qps(xb_host, xq_host, k, budget_s, steps=1, warmup=0):
             # bounded: stop when the next run would exceed the budget (at least one timed run)
             if ts and (time.time() - t_begin) + dt > budget_s:
                 break
-        t = float(np.mean(ts))
-        return ns / t, {"kind": "reference", "cores": cores, "sample": "IndexFlatL2 (oracle/_ref, %s, OpenBLAS pthreads) full N=%d, first %d of %d queries, k=%d; %.2f s/step over %d timed step(s) (%d run); add %.1f s" % (
-            ref.compile_options().strip(), xb_host.shape[0], ns, xq_host.shape[0], k, t, len(ts), n_runs, t_add), "ms_per_step": t * 1e3, "nq_sample": ns}
+        t_meas = float(np.mean(ts))
+        t = t_meas * (nfull / nrows)  # exhaustive search: time linear in the rows scanned
+        return ns / t, {"kind": "reference", "cores": cores, "sample": "IndexFlatL2 (oracle/_ref, %s, OpenBLAS pthreads, %d threads) first %d of %d queries, k=%d, against the first %d of N=%d rows: %.2f s measured/step over %d timed step(s) (%d run), scaled x%.0f to full N (exhaustive search is linear in N) = %.2f s/step; add %.1f s" % (
+            ref.compile_options().strip(), cores, ns, xq_host.shape[0], k, nrows, nfull, t_meas, len(ts), n_runs, nfull / nrows, t, t_add), "ms_per_step": t * 1e3, "nq_sample": ns}
     from oracle import oracle_np as o
 
     nb = min(xb_host.shape[0], 200_000)

@@ -71,6 +71,22 @@ def set_omp_threads(n):
     lib().ref_omp_set_threads(int(n))
 
 
+def set_blas_threads(n):
+    """OpenBLAS (pthreads build) sizes its pool from the visible CPUs; inside a CPU-quota cgroup that
+    oversubscribes badly.  Best effort: openblas_set_num_threads through the already-loaded library."""
+    lib()
+    try:
+        for line in open("/proc/self/maps"):
+            if "libopenblas" in line:
+                path = line.split()[-1]
+                L = ctypes.CDLL(path)
+                L.openblas_set_num_threads(int(n))
+                return True
+    except Exception:
+        pass
+    return False
+
+
 def compile_options():
     return lib().ref_compile_options().decode()
 
