@@ -1037,7 +1037,8 @@ void GpuIndexIVFFlat::scanImpl_(
         idx_t* iDev) const {
     runIvfFlatScan(
             resources_.get(), config_.device, xDev, n, d, probes, np, lists_->dStart(), lists_->dLen(),
-            reinterpret_cast<const float*>(lists_->codes()), lists_->ids(), k, metric_type, dDev, iDev, stream_());
+            reinterpret_cast<const float*>(lists_->codes()), lists_->ids(), lists_->arenaElems(), k, metric_type, dDev,
+            iDev, stream_());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1193,8 +1194,8 @@ void GpuIndexIVFPQ::scanImpl_(
     if (lists_->interleaved()) {
         runIvfPqScanInterleaved(
                 resources_.get(), config_.device, xDev, n, d, probes, coarseDis, np, quantizer->vectorsDevice(),
-                pqCentroidsT_.data(), M_, lists_->dStart(), lists_->dLen(), lists_->codes(), lists_->ids(), k,
-                metric_type, dDev, iDev, stream_());
+                pqCentroidsT_.data(), M_, lists_->dStart(), lists_->dLen(), lists_->codes(), lists_->ids(),
+                lists_->arenaElems(), k, metric_type, dDev, iDev, stream_());
         return;
     }
     runIvfPqScan(

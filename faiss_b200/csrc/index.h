@@ -326,6 +326,9 @@ class IvfLists {
         return codeSize_;
     }
     int maxListLength() const;
+    int64_t arenaElems() const {
+        return arenaElems_;
+    }
     bool interleaved() const {
         return interleaved_;
     }

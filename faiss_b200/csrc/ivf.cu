@@ -284,8 +284,9 @@ void runIvfScatter(
 constexpr int kScanWarps = 4;
 constexpr int kScanBuf = 64;
 
+template <typename IdT>
 __device__ void block_merge_and_write(
-        WarpTopK<int>& w,
+        WarpTopK<IdT>& w,
         int warp,
         unsigned char* smemLists,
         size_t perWarp,
@@ -300,13 +301,13 @@ __device__ void block_merge_and_write(
     if (warp == 0) {
         for (int ow = 1; ow < kScanWarps; ow++) {
             const float* ok = reinterpret_cast<const float*>(smemLists + perWarp * ow);
-            const int* oi = reinterpret_cast<const int*>(smemLists + perWarp * ow + sizeof(float) * (LIST + kScanBuf));
+            const IdT* oi = reinterpret_cast<const IdT*>(smemLists + perWarp * ow + sizeof(float) * (LIST + kScanBuf));
             for (int e0 = 0; e0 < k; e0 += 32) {
                 int e = e0 + lane_id();
                 bool valid = e < k;
                 float key = valid ? ok[e] : 0.f;
-                int id = valid ? oi[e] : 0;
-                valid = valid && id != IdLimits<int>::max();
+                IdT id = valid ? oi[e] : 0;
+                valid = valid && id != IdLimits<IdT>::max();
                 if (!__any_sync(kFullMask, valid && key <= w.thr))
                     break; // sorted: nothing further can enter
                 w.add(valid, key, id);
@@ -314,8 +315,8 @@ __device__ void block_merge_and_write(
         }
         w.finish();
         for (int j = lane_id(); j < k; j += 32) {
-            int id = w.q.ids[j];
-            bool ok2 = id != IdLimits<int>::max();
+            IdT id = w.q.ids[j];
+            bool ok2 = id != IdLimits<IdT>::max();
             outD[j] = ok2 ? w.q.keys[j] + addToKey : CUDART_INF_F;
             outI[j] = ok2 ? (ids ? ids[id] : (idx_t)id) : -1;
         }
@@ -323,48 +324,42 @@ __device__ void block_merge_and_write(
 }
 
 // ------------------------------------------------------------------------------------------
-// IVF-Flat scan: block per (query, probe)
+// IVF-Flat scan: block per (query, chunk of its probes).  The per-warp top-k lists and thresholds live
+// across the probes of the chunk (list ids = arena positions), so threshold passes grow with
+// log(vectors per CTA) instead of with the number of (query, probe) pairs.
 // ------------------------------------------------------------------------------------------
-template <bool IS_L2>
+template <bool IS_L2, typename IdT>
 __global__ void __launch_bounds__(kScanWarps * 32) ivfflat_scan_kernel(
         const float* __restrict__ Q,
         int d,
         const idx_t* __restrict__ probes,
         int nprobe,
+        int probesPerCta,
         const int64_t* __restrict__ listStart,
         const int* __restrict__ listLen,
         const float* __restrict__ arenaVecs,
         const idx_t* __restrict__ arenaIds,
         int k,
         int LIST,
-        float* __restrict__ partD, // [nq, nprobe, k] keys
+        float* __restrict__ partD, // [nq, chunks, k] keys
         idx_t* __restrict__ partI) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int q = blockIdx.y, p = blockIdx.x;
+    const int q = blockIdx.y, chunk = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     float* qs = reinterpret_cast<float*>(smem_raw); // [d]
     unsigned char* lists = smem_raw + round_up(sizeof(float) * d, 16);
-    const size_t perWarp = SmemTopK<int>::bytes(LIST, kScanBuf);
-    float* oD = partD + ((int64_t)q * nprobe + p) * k;
-    idx_t* oI = partI + ((int64_t)q * nprobe + p) * k;
+    const size_t perWarp = SmemTopK<IdT>::bytes(LIST, kScanBuf);
+    float* oD = partD + ((int64_t)q * gridDim.x + chunk) * k;
+    idx_t* oI = partI + ((int64_t)q * gridDim.x + chunk) * k;
 
-    const idx_t l = probes[(int64_t)q * nprobe + p];
-    if (l < 0) { // NaN query / missing probe (PQScanMultiPassNoPrecomputed-inl.cuh:199-202)
-        for (int j = threadIdx.x; j < k; j += blockDim.x) {
-            oD[j] = CUDART_INF_F;
-            oI[j] = -1;
-        }
-        return;
-    }
     for (int i = threadIdx.x; i < d; i += blockDim.x)
         qs[i] = Q[(int64_t)q * d + i];
-    WarpTopK<int> w;
+    WarpTopK<IdT> w;
     unsigned char* mine = lists + perWarp * warp;
-    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<int*>(mine + sizeof(float) * (LIST + kScanBuf)), LIST, kScanBuf, k);
+    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<IdT*>(mine + sizeof(float) * (LIST + kScanBuf)), LIST, kScanBuf, k);
     __syncthreads();
+    const int pBegin = chunk * probesPerCta, pEnd = min(nprobe, pBegin + probesPerCta);
 
-    const int len = listLen[l];
-    const float* base = arenaVecs + listStart[l] * d;
     if ((d & 127) == 0 && d <= 512) {
         // Fast path (d multiple of 128): lane t owns dims [128c + 4t, +4) for c < d/128, kept in registers.
         // A group of 32 vectors = 32 x d/128 coalesced 128-bit loads per lane, issued 8 vectors at a time
@@ -375,84 +370,135 @@ __global__ void __launch_bounds__(kScanWarps * 32) ivfflat_scan_kernel(
 #pragma unroll
         for (int c = 0; c < 4; c++)
             qv[c] = c < nch ? *reinterpret_cast<const float4*>(qs + c * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int v0 = warp * 32; v0 < len; v0 += kScanWarps * 32) {
-            float vals[32];
+        for (int p = pBegin; p < pEnd; p++) {
+            const idx_t l = probes[(int64_t)q * nprobe + p];
+            if (l < 0) // NaN query / missing probe (PQScanMultiPassNoPrecomputed-inl.cuh:199-202)
+                continue;
+            const int len = listLen[l];
+            const int64_t ls = listStart[l];
+            const float* base = arenaVecs + ls * d;
+            for (int v0 = warp * 32; v0 < len; v0 += kScanWarps * 32) {
+                float vals[32];
 #pragma unroll
-            for (int b8 = 0; b8 < 4; b8++) {
-                float4 y[8];
+                for (int b8 = 0; b8 < 4; b8++) {
+                    float4 y[8];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (c < nch) {
+                    for (int c = 0; c < 4; c++) {
+                        if (c < nch) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int v = min(v0 + b8 * 8 + j, len - 1); // clamped tail, masked at add()
-                            y[j] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)v * d + c * 128) + lane);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float acc = c == 0 ? 0.f : vals[b8 * 8 + j];
-                            if (IS_L2) {
-                                float d0 = qv[c].x - y[j].x, d1 = qv[c].y - y[j].y, d2 = qv[c].z - y[j].z, d3 = qv[c].w - y[j].w;
-                                acc = fmaf(d0, d0, acc);
-                                acc = fmaf(d1, d1, acc);
-                                acc = fmaf(d2, d2, acc);
-                                acc = fmaf(d3, d3, acc);
-                            } else {
-                                acc = fmaf(qv[c].x, y[j].x, acc);
-                                acc = fmaf(qv[c].y, y[j].y, acc);
-                                acc = fmaf(qv[c].z, y[j].z, acc);
-                                acc = fmaf(qv[c].w, y[j].w, acc);
+                            for (int j = 0; j < 8; j++) {
+                                const int v = min(v0 + b8 * 8 + j, len - 1); // clamped tail, masked at add()
+                                y[j] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)v * d + c * 128) + lane);
                             }
-                            vals[b8 * 8 + j] = acc;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                float acc = c == 0 ? 0.f : vals[b8 * 8 + j];
+                                if (IS_L2) {
+                                    float d0 = qv[c].x - y[j].x, d1 = qv[c].y - y[j].y, d2 = qv[c].z - y[j].z, d3 = qv[c].w - y[j].w;
+                                    acc = fmaf(d0, d0, acc);
+                                    acc = fmaf(d1, d1, acc);
+                                    acc = fmaf(d2, d2, acc);
+                                    acc = fmaf(d3, d3, acc);
+                                } else {
+                                    acc = fmaf(qv[c].x, y[j].x, acc);
+                                    acc = fmaf(qv[c].y, y[j].y, acc);
+                                    acc = fmaf(qv[c].z, y[j].z, acc);
+                                    acc = fmaf(qv[c].w, y[j].w, acc);
+                                }
+                                vals[b8 * 8 + j] = acc;
+                            }
                         }
                     }
                 }
-            }
-            // transposing butterfly: afterwards lane t holds the full sum of vector v0 + t
+                // transposing butterfly: afterwards lane t holds the full sum of vector v0 + t
 #pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) {
+                for (int s = 16; s >= 1; s >>= 1) {
 #pragma unroll
-                for (int j = 0; j < s; j++) {
-                    const bool up = (lane & s) != 0;
-                    const float send = up ? vals[j] : vals[j + s];
-                    const float keep = up ? vals[j + s] : vals[j];
-                    vals[j] = keep + __shfl_xor_sync(kFullMask, send, s);
+                    for (int j = 0; j < s; j++) {
+                        const bool up = (lane & s) != 0;
+                        const float send = up ? vals[j] : vals[j + s];
+                        const float keep = up ? vals[j + s] : vals[j];
+                        vals[j] = keep + __shfl_xor_sync(kFullMask, send, s);
+                    }
                 }
+                w.add(v0 + lane < len, IS_L2 ? vals[0] : -vals[0], (IdT)(ls + v0 + lane));
             }
-            w.add(v0 + lane < len, IS_L2 ? vals[0] : -vals[0], v0 + lane);
         }
-        block_merge_and_write(w, warp, lists, perWarp, LIST, k, arenaIds + listStart[l], 0.f, oD, oI);
+        block_merge_and_write<IdT>(w, warp, lists, perWarp, LIST, k, arenaIds, 0.f, oD, oI);
         return;
     }
     // generic path: each warp takes groups of 32 vectors; lanes stride the dimension
-    for (int v0 = warp * 32; v0 < len; v0 += kScanWarps * 32) {
-        float mineKey = 0.f;
-        const int cntv = min(32, len - v0);
-        for (int v = 0; v < cntv; v++) {
-            const float* row = base + (int64_t)(v0 + v) * d;
-            float acc = 0.f;
-            for (int i = lane; i < d; i += 32) {
-                float a = qs[i], b = row[i];
-                if (IS_L2) {
-                    float df = a - b;
-                    acc = fmaf(df, df, acc);
-                } else {
-                    acc = fmaf(a, b, acc);
+    for (int p = pBegin; p < pEnd; p++) {
+        const idx_t l = probes[(int64_t)q * nprobe + p];
+        if (l < 0)
+            continue;
+        const int len = listLen[l];
+        const int64_t ls = listStart[l];
+        const float* base = arenaVecs + ls * d;
+        for (int v0 = warp * 32; v0 < len; v0 += kScanWarps * 32) {
+            float mineKey = 0.f;
+            const int cntv = min(32, len - v0);
+            for (int v = 0; v < cntv; v++) {
+                const float* row = base + (int64_t)(v0 + v) * d;
+                float acc = 0.f;
+                for (int i = lane; i < d; i += 32) {
+                    float a = qs[i], b = row[i];
+                    if (IS_L2) {
+                        float df = a - b;
+                        acc = fmaf(df, df, acc);
+                    } else {
+                        acc = fmaf(a, b, acc);
+                    }
                 }
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                acc += __shfl_xor_sync(kFullMask, acc, o);
-            if (lane == v)
-                mineKey = IS_L2 ? acc : -acc;
+                for (int o = 16; o > 0; o >>= 1)
+                    acc += __shfl_xor_sync(kFullMask, acc, o);
+                if (lane == v)
+                    mineKey = IS_L2 ? acc : -acc;
+            }
+            w.add(lane < cntv, mineKey, (IdT)(ls + v0 + lane));
         }
-        w.add(lane < cntv, mineKey, v0 + lane);
     }
-    block_merge_and_write(w, warp, lists, perWarp, LIST, k, arenaIds + listStart[l], 0.f, oD, oI);
+    block_merge_and_write<IdT>(w, warp, lists, perWarp, LIST, k, arenaIds, 0.f, oD, oI);
 }
 
 void runMergeTopKKeyspace(
         const float*, const idx_t*, int64_t, int, int, int, MetricType, int64_t, float*, idx_t*, cudaStream_t);
+
+// CTAs per query: 1 when the queries alone fill the machine several times over, else the probes are
+// split so that ~8 CTAs per SM exist
+int ivfScanChunks(int device, int64_t nq, int nprobe, int* probesPerCta) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t wantCtas = (int64_t)sms * 8;
+    int chunks = (int)std::min<int64_t>(nprobe, std::max<int64_t>(1, ceil_div(wantCtas, nq)));
+    *probesPerCta = ceil_div(nprobe, chunks);
+    return ceil_div(nprobe, *probesPerCta);
+}
+
+template <bool IS_L2, typename IdT>
+static void launchIvfFlatScan(
+        dim3 grid,
+        size_t smem,
+        cudaStream_t stream,
+        const float* Q,
+        int d,
+        const idx_t* probes,
+        int nprobe,
+        int probesPerCta,
+        const int64_t* listStart,
+        const int* listLen,
+        const float* arenaVecs,
+        const idx_t* arenaIds,
+        int k,
+        int LIST,
+        float* partD,
+        idx_t* partI) {
+    auto kern = ivfflat_scan_kernel<IS_L2, IdT>;
+    CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanWarps * 32, smem, stream>>>(
+            Q, d, probes, nprobe, probesPerCta, listStart, listLen, arenaVecs, arenaIds, k, LIST, partD, partI);
+}
 
 void runIvfFlatScan(
         GpuResources* res,
@@ -466,6 +512,7 @@ void runIvfFlatScan(
         const int* listLen,
         const float* arenaVecs,
         const idx_t* arenaIds,
+        int64_t arenaElems,
         int k,
         MetricType metric,
         float* outD,
@@ -474,33 +521,41 @@ void runIvfFlatScan(
     if (nq == 0)
         return;
     const int LIST = std::max(64, next_pow2(k));
-    size_t smem = round_up(sizeof(float) * d, 16) + SmemTopK<int>::bytes(LIST, kScanBuf) * kScanWarps;
+    const bool wide = arenaElems >= (int64_t(1) << 31) - 1;
+    const size_t listBytes = wide ? SmemTopK<long long>::bytes(LIST, kScanBuf) : SmemTopK<int>::bytes(LIST, kScanBuf);
+    size_t smem = round_up(sizeof(float) * d, 16) + listBytes * kScanWarps;
     FB_THROW_IF_NOT_MSG(smem <= 200 * 1024, "k / d too large for the IVF-Flat scan kernel");
+    int probesPerCta = 1;
+    const int chunks = ivfScanChunks(device, nq, nprobe, &probesPerCta);
     // query batches bound the partial-result scratch
-    const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)nprobe * k * 12)));
+    const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)chunks * k * 12)));
+    const bool l2 = metric == METRIC_L2;
     for (int64_t q0 = 0; q0 < nq; q0 += maxQ) {
         int64_t nb = std::min(maxQ, nq - q0);
-        auto partD = res->temp(device, sizeof(float) * nb * nprobe * k);
-        auto partI = res->temp(device, sizeof(idx_t) * nb * nprobe * k);
-        dim3 grid((unsigned)nprobe, (unsigned)nb);
+        auto partD = res->temp(device, sizeof(float) * nb * chunks * k);
+        auto partI = res->temp(device, sizeof(idx_t) * nb * chunks * k);
+        dim3 grid((unsigned)chunks, (unsigned)nb);
         KernelTiming::begin("ivfflat_scan", stream);
-        if (metric == METRIC_L2) {
-            CUDA_VERIFY(cudaFuncSetAttribute(
-                    ivfflat_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ivfflat_scan_kernel<true><<<grid, kScanWarps * 32, smem, stream>>>(
-                    Q + q0 * d, d, probes + q0 * nprobe, nprobe, listStart, listLen, arenaVecs, arenaIds, k, LIST,
-                    partD.as<float>(), partI.as<idx_t>());
+#define SCAN(L2_, ID_)                                                                                            \
+    launchIvfFlatScan<L2_, ID_>(                                                                                  \
+            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, nprobe, probesPerCta, listStart, listLen,   \
+            arenaVecs, arenaIds, k, LIST, partD.as<float>(), partI.as<idx_t>())
+        if (l2) {
+            if (wide)
+                SCAN(true, long long);
+            else
+                SCAN(true, int);
         } else {
-            CUDA_VERIFY(cudaFuncSetAttribute(
-                    ivfflat_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ivfflat_scan_kernel<false><<<grid, kScanWarps * 32, smem, stream>>>(
-                    Q + q0 * d, d, probes + q0 * nprobe, nprobe, listStart, listLen, arenaVecs, arenaIds, k, LIST,
-                    partD.as<float>(), partI.as<idx_t>());
+            if (wide)
+                SCAN(false, long long);
+            else
+                SCAN(false, int);
         }
+#undef SCAN
         KernelTiming::end("ivfflat_scan", stream);
         CUDA_CHECK_LAST();
         runMergeTopKKeyspace(
-                partD.as<float>(), partI.as<idx_t>(), nb, nprobe, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
+                partD.as<float>(), partI.as<idx_t>(), nb, chunks, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
     }
 }
 

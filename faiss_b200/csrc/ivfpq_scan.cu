@@ -20,10 +20,11 @@ namespace fb200 {
 
 void runMergeTopKKeyspace(
         const float*, const idx_t*, int64_t, int, int, int, MetricType, int64_t, float*, idx_t*, cudaStream_t);
+int ivfScanChunks(int device, int64_t nq, int nprobe, int* probesPerCta);
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 8;
 constexpr int kBuf = 64;
 constexpr int kLutSlots = 64; // 256 B per code value
 
@@ -77,16 +78,17 @@ __global__ void pq_list_from_interleaved_kernel(const uint8_t* __restrict__ src,
     flat[v * M + ((j + (int)(v & 31)) % M)] = src[interleaved_pos(v, j, M)];
 }
 
-// block-level merge of the per-warp lists into warp 0 + write-out (same contract as ivf.cu)
+// block-level merge of the per-warp lists into warp 0 + write-out.  List ids are arena positions;
+// the user labels are looked up only for the k survivors.
+template <typename IdT>
 __device__ void merge_and_write(
-        WarpTopK<int>& w,
+        WarpTopK<IdT>& w,
         int warp,
         unsigned char* lists,
         size_t perWarp,
         int LIST,
         int k,
-        const idx_t* __restrict__ ids,
-        float addToKey,
+        const idx_t* __restrict__ arenaIds,
         float* __restrict__ outD,
         idx_t* __restrict__ outI) {
     w.finish();
@@ -94,13 +96,13 @@ __device__ void merge_and_write(
     if (warp == 0) {
         for (int ow = 1; ow < kWarps; ow++) {
             const float* ok = reinterpret_cast<const float*>(lists + perWarp * ow);
-            const int* oi = reinterpret_cast<const int*>(lists + perWarp * ow + sizeof(float) * (LIST + kBuf));
+            const IdT* oi = reinterpret_cast<const IdT*>(lists + perWarp * ow + sizeof(float) * (LIST + kBuf));
             for (int e0 = 0; e0 < k; e0 += 32) {
                 int e = e0 + lane_id();
                 bool valid = e < k;
                 float key = valid ? ok[e] : 0.f;
-                int id = valid ? oi[e] : 0;
-                valid = valid && id != IdLimits<int>::max();
+                IdT id = valid ? oi[e] : 0;
+                valid = valid && id != IdLimits<IdT>::max();
                 if (!__any_sync(kFullMask, valid && key <= w.thr))
                     break;
                 w.add(valid, key, id);
@@ -108,21 +110,26 @@ __device__ void merge_and_write(
         }
         w.finish();
         for (int j = lane_id(); j < k; j += 32) {
-            int id = w.q.ids[j];
-            bool ok2 = id != IdLimits<int>::max();
-            outD[j] = ok2 ? w.q.keys[j] + addToKey : CUDART_INF_F;
-            outI[j] = ok2 ? ids[id] : -1;
+            IdT id = w.q.ids[j];
+            bool ok2 = id != IdLimits<IdT>::max();
+            outD[j] = ok2 ? w.q.keys[j] : CUDART_INF_F;
+            outI[j] = ok2 ? arenaIds[id] : -1;
         }
     }
 }
 
-template <int M, bool IS_L2>
+// One CTA = one query x one chunk of its probes.  The per-warp top-k lists (and their thresholds)
+// live across the probes of the chunk, so the number of candidates that pass the threshold grows with
+// log(vectors scanned per CTA), not with the number of (query, probe) pairs; per probe only the LUT is
+// rebuilt.  Keys: L2 -> sum of LUT entries; IP -> -(q.centroid) - sum (coarse term folded in per probe).
+template <int M, bool IS_L2, typename IdT>
 __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
         const idx_t* __restrict__ probes,
         const float* __restrict__ coarseDis,
         int nprobe,
+        int probesPerCta,
         const float* __restrict__ coarse,
         const float* __restrict__ pqT, // [256][M][dsub]
         const int64_t* __restrict__ listStart,
@@ -134,98 +141,119 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         float* __restrict__ partD,
         idx_t* __restrict__ partI) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int q = blockIdx.y, p = blockIdx.x;
+    const int q = blockIdx.y, chunk = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int dsub = d / M;
     float* lut = reinterpret_cast<float*>(smem_raw);                 // [256][kLutSlots]
     float* rs = lut + 256 * kLutSlots;                               // [d]
     unsigned char* lists = reinterpret_cast<unsigned char*>(rs) + round_up(sizeof(float) * d, 16);
-    const size_t perWarp = SmemTopK<int>::bytes(LIST, kBuf);
-    float* oD = partD + ((int64_t)q * nprobe + p) * k;
-    idx_t* oI = partI + ((int64_t)q * nprobe + p) * k;
+    const size_t perWarp = SmemTopK<IdT>::bytes(LIST, kBuf);
+    float* oD = partD + ((int64_t)q * gridDim.x + chunk) * k;
+    idx_t* oI = partI + ((int64_t)q * gridDim.x + chunk) * k;
 
-    const idx_t l = probes[(int64_t)q * nprobe + p];
-    if (l < 0) {
-        for (int j = threadIdx.x; j < k; j += blockDim.x) {
-            oD[j] = CUDART_INF_F;
-            oI[j] = -1;
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        float v = Q[(int64_t)q * d + i];
-        rs[i] = IS_L2 ? v - coarse[l * d + i] : v;
-    }
-    WarpTopK<int> w;
+    WarpTopK<IdT> w;
     unsigned char* mine = lists + perWarp * warp;
-    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<int*>(mine + sizeof(float) * (LIST + kBuf)), LIST, kBuf, k);
-    __syncthreads();
-    // ---- LUT: entry (c, m) -> slots m, m+M, ... (< 64).  e = c*M + m: coalesced pqT reads, conflict-free writes
-    for (int e = threadIdx.x; e < 256 * M; e += blockDim.x) {
-        const int c = e / M, m = e - c * M;
-        const float* cp = pqT + (size_t)e * dsub;
-        const float* rp = rs + m * dsub;
-        float acc = 0.f;
-        for (int j = 0; j < dsub; j++) {
-            if (IS_L2) {
-                float df = rp[j] - cp[j];
-                acc = fmaf(df, df, acc);
-            } else {
-                acc = fmaf(rp[j], cp[j], acc);
-            }
-        }
-        const float val = IS_L2 ? acc : -acc;
-#pragma unroll
-        for (int s = 0; s < kLutSlots; s += M)
-            lut[c * kLutSlots + s + m] = val;
-    }
-    __syncthreads();
-
-    const int len = listLen[l];
-    const uint8_t* codes = arenaCodes + listStart[l] * (int64_t)M;
+    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<IdT*>(mine + sizeof(float) * (LIST + kBuf)), LIST, kBuf, k);
     const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
     const unsigned lane4 = (unsigned)lane << 2;
-    const int ngroups = (len + 31) >> 5;
-    // kU groups per iteration: all of a lane's 128-bit loads are issued before the first lookup, so each
-    // warp keeps kU * M/16 * 512 B in flight (memory-level parallelism for the HBM stream)
-    constexpr int kU = 4;
-    for (int g0 = warp * kU; g0 < ngroups; g0 += kWarps * kU) {
-        uint4 c4[kU][M / 16];
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
-            const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-#pragma unroll
-            for (int h = 0; h < M / 16; h++)
-                c4[u][h] = __ldg(gp + h * 32);
+
+    const int pEnd = min(nprobe, (chunk + 1) * probesPerCta);
+    for (int p = chunk * probesPerCta; p < pEnd; p++) {
+        const idx_t l = probes[(int64_t)q * nprobe + p];
+        if (l < 0)
+            continue; // block-uniform
+        __syncthreads(); // every warp is done with the previous probe's LUT
+        for (int i = threadIdx.x; i < d; i += blockDim.x) {
+            float v = Q[(int64_t)q * d + i];
+            rs[i] = IS_L2 ? v - coarse[l * d + i] : v;
         }
-#pragma unroll
-        for (int u = 0; u < kU; u++) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int h = 0; h < M / 16; h++) {
-                const unsigned wds[4] = {c4[u][h].x, c4[u][h].y, c4[u][h].z, c4[u][h].w};
-#pragma unroll
-                for (int wi = 0; wi < 4; wi++) {
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int j = h * 16 + wi * 4 + b;
-                        // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
-                        const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
-                        const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
-                        if (j & 1)
-                            a1 += val;
-                        else
-                            a0 += val;
+        __syncthreads();
+        // ---- LUT: entry (c, m) -> slots m, m+M, ... (< 64).  e = c*M + m: coalesced pqT reads, conflict-free writes
+        for (int e = threadIdx.x; e < 256 * M; e += blockDim.x) {
+            const int c = e / M, m = e - c * M;
+            const float* cp = pqT + (size_t)e * dsub;
+            const float* rp = rs + m * dsub;
+            float acc = 0.f;
+            if ((dsub & 3) == 0) {
+                for (int j = 0; j < dsub; j += 4) {
+                    const float4 cv = __ldg(reinterpret_cast<const float4*>(cp + j));
+                    const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+                    if (IS_L2) {
+                        float d0 = rv.x - cv.x, d1 = rv.y - cv.y, d2 = rv.z - cv.z, d3 = rv.w - cv.w;
+                        acc = fmaf(d0, d0, acc);
+                        acc = fmaf(d1, d1, acc);
+                        acc = fmaf(d2, d2, acc);
+                        acc = fmaf(d3, d3, acc);
+                    } else {
+                        acc = fmaf(rv.x, cv.x, acc);
+                        acc = fmaf(rv.y, cv.y, acc);
+                        acc = fmaf(rv.z, cv.z, acc);
+                        acc = fmaf(rv.w, cv.w, acc);
+                    }
+                }
+            } else {
+                for (int j = 0; j < dsub; j++) {
+                    if (IS_L2) {
+                        float df = rp[j] - cp[j];
+                        acc = fmaf(df, df, acc);
+                    } else {
+                        acc = fmaf(rp[j], cp[j], acc);
                     }
                 }
             }
-            const int v = (g0 + u) * 32 + lane;
-            w.add(g0 + u < ngroups && v < len, a0 + a1, v);
+            const float val = IS_L2 ? acc : -acc;
+#pragma unroll
+            for (int s = 0; s < kLutSlots; s += M)
+                lut[c * kLutSlots + s + m] = val;
+        }
+        __syncthreads();
+
+        const int len = listLen[l];
+        const int64_t ls = listStart[l];
+        const uint8_t* codes = arenaCodes + ls * (int64_t)M;
+        const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
+        const int ngroups = (len + 31) >> 5;
+        // kU groups per iteration: all of a lane's 128-bit loads are issued before the first lookup, so each
+        // warp keeps kU * M/16 * 512 B in flight (memory-level parallelism for the HBM stream)
+        constexpr int kU = 4;
+        for (int g0 = warp * kU; g0 < ngroups; g0 += kWarps * kU) {
+            uint4 c4[kU][M / 16];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
+                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+#pragma unroll
+                for (int h = 0; h < M / 16; h++)
+                    c4[u][h] = __ldg(gp + h * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int h = 0; h < M / 16; h++) {
+                    const unsigned wds[4] = {c4[u][h].x, c4[u][h].y, c4[u][h].z, c4[u][h].w};
+#pragma unroll
+                    for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int j = h * 16 + wi * 4 + b;
+                            // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
+                            const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
+                            const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
+                            if (j & 1)
+                                a1 += val;
+                            else
+                                a0 += val;
+                        }
+                    }
+                }
+                const int v = (g0 + u) * 32 + lane;
+                const float key = IS_L2 ? a0 + a1 : (a0 + a1) + add;
+                w.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
+            }
         }
     }
-    const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
-    merge_and_write(w, warp, lists, perWarp, LIST, k, arenaIds + listStart[l], add, oD, oI);
+    merge_and_write<IdT>(w, warp, lists, perWarp, LIST, k, arenaIds, oD, oI);
 }
 
 } // namespace
@@ -263,7 +291,7 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2>
+template <int M, bool IS_L2, typename IdT>
 static void launchScan(
         dim3 grid,
         size_t smem,
@@ -273,6 +301,7 @@ static void launchScan(
         const idx_t* probes,
         const float* coarseDis,
         int nprobe,
+        int probesPerCta,
         const float* coarse,
         const float* pqT,
         const int64_t* listStart,
@@ -283,11 +312,12 @@ static void launchScan(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
-            Q, d, probes, coarseDis, nprobe, coarse, pqT, listStart, listLen, codes, ids, k, LIST, partD, partI);
+            Q, d, probes, coarseDis, nprobe, probesPerCta, coarse, pqT, listStart, listLen, codes, ids, k, LIST, partD,
+            partI);
     KernelTiming::end("ivfpq_scan", stream);
     CUDA_CHECK_LAST();
 }
@@ -308,6 +338,7 @@ void runIvfPqScanInterleaved(
         const int* listLen,
         const uint8_t* arenaCodes,
         const idx_t* arenaIds,
+        int64_t arenaElems,
         int k,
         MetricType metric,
         float* outD,
@@ -317,33 +348,46 @@ void runIvfPqScanInterleaved(
         return;
     FB_THROW_IF_NOT(ivfPqInterleavedSupported(M));
     const int LIST = std::max(64, next_pow2(k));
-    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + SmemTopK<int>::bytes(LIST, kBuf) * kWarps;
+    const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
+    const size_t listBytes = wide ? SmemTopK<long long>::bytes(LIST, kBuf) : SmemTopK<int>::bytes(LIST, kBuf);
+    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * kWarps;
     FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
-    const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)nprobe * k * 12)));
     const bool l2 = metric == METRIC_L2;
+    int probesPerCta = 1;
+    const int chunks = ivfScanChunks(device, nq, nprobe, &probesPerCta);
+    const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)chunks * k * 12)));
     for (int64_t q0 = 0; q0 < nq; q0 += maxQ) {
         int64_t nb = std::min(maxQ, nq - q0);
-        auto partD = res->temp(device, sizeof(float) * nb * nprobe * k);
-        auto partI = res->temp(device, sizeof(idx_t) * nb * nprobe * k);
-        dim3 grid((unsigned)nprobe, (unsigned)nb);
-#define SCAN(M_, L2_)                                                                                              \
-    launchScan<M_, L2_>(                                                                                           \
-            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, coarseCentroids, \
-            pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(), partI.as<idx_t>())
+        auto partD = res->temp(device, sizeof(float) * nb * chunks * k);
+        auto partI = res->temp(device, sizeof(idx_t) * nb * chunks * k);
+        dim3 grid((unsigned)chunks, (unsigned)nb);
+#define SCAN(M_, L2_, ID_)                                                                                         \
+    launchScan<M_, L2_, ID_>(                                                                                      \
+            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
+            coarseCentroids, pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(),   \
+            partI.as<idx_t>())
+#define SCAN_ID(M_, L2_)        \
+    do {                        \
+        if (wide)               \
+            SCAN(M_, L2_, long long); \
+        else                    \
+            SCAN(M_, L2_, int); \
+    } while (0)
         if (M == 32) {
             if (l2)
-                SCAN(32, true);
+                SCAN_ID(32, true);
             else
-                SCAN(32, false);
+                SCAN_ID(32, false);
         } else {
             if (l2)
-                SCAN(16, true);
+                SCAN_ID(16, true);
             else
-                SCAN(16, false);
+                SCAN_ID(16, false);
         }
+#undef SCAN_ID
 #undef SCAN
         runMergeTopKKeyspace(
-                partD.as<float>(), partI.as<idx_t>(), nb, nprobe, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
+                partD.as<float>(), partI.as<idx_t>(), nb, chunks, k, k, metric, 0, outD + q0 * k, outI + q0 * k, stream);
     }
 }
 

@@ -209,6 +209,7 @@ void runIvfFlatScan(
         const int* listLen,
         const float* arenaVecs,
         const idx_t* arenaIds,
+        int64_t arenaElems,
         int k,
         MetricType metric,
         float* outD,
@@ -287,6 +288,7 @@ void runIvfPqScanInterleaved(
         const int* listLen,
         const uint8_t* arenaCodes,
         const idx_t* arenaIds,
+        int64_t arenaElems,
         int k,
         MetricType metric,
         float* outD,

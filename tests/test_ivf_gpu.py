@@ -140,6 +140,43 @@ def test_ivfpq_train_add_search_vs_oracle(res, M):
     assert np.array_equal(I, I3)
 
 
+@pytest.mark.parametrize("kind", ["flat40", "flat128", "pq16", "pq32"])
+def test_ivf_scan_batch_size_invariance(res, kind):
+    """The scan kernels give a CTA one query x a chunk of its probes; the chunk size depends on the
+    batch size (1 probe per CTA for small batches, all probes for large ones).  The results must not:
+    a 3000-query batch (one CTA per query), 400-query batches (3 probes per CTA) and 50-query batches
+    (1 probe per CTA) are compared bit for bit."""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(11)
+    N, nlist, nq, k, nprobe = 40000, 64, 3000, 50, 9
+    d = {"flat40": 40, "flat128": 128, "pq16": 64, "pq32": 64}[kind]
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    if kind.startswith("flat"):
+        idx = fb.GpuIndexIVFFlat(res, d, nlist, 1)
+    else:
+        idx = fb.GpuIndexIVFPQ(res, d, nlist, int(kind[2:]), 8, 1)
+        idx.setClustering(niter=4)
+        idx.setPQClustering(niter=4)
+    idx.train(xb[:20000])
+    idx.add(xb)
+    idx.nprobe = nprobe
+    D, I = idx.search(xq, k)
+    for bs in (400, 50):
+        for q0 in (0, 1200, nq - bs):
+            Db, Ib = idx.search(xq[q0 : q0 + bs], k)
+            assert np.array_equal(Db, D[q0 : q0 + bs])
+            # ids may only differ inside runs of exactly tied distances
+            diff = Ib != I[q0 : q0 + bs]
+            if diff.any():
+                Dq = D[q0 : q0 + bs]
+                tied = np.zeros_like(diff)
+                tied[:, 1:] |= Dq[:, 1:] == Dq[:, :-1]
+                tied[:, :-1] |= Dq[:, :-1] == Dq[:, 1:]
+                assert not (diff & ~tied).any()
+
+
 def test_ivfpq_constraints(res):
     import faiss_b200 as fb
 
