@@ -151,6 +151,7 @@ __global__ void tc_select_kernel(
         int k,
         int LIST,
         int slices,
+        int parts,
         const uint2* __restrict__ cand,
         int cap,
         const int* __restrict__ candCount,
@@ -184,8 +185,8 @@ __global__ void tc_select_kernel(
     const int qPairs = (nq + kPairM - 1) / kPairM;
     for (int s = 0; s < slices; s++) {
         const int u = s * qPairs + pair;
-        for (int h = 0; h < 2; h++) {
-            const long long seg = ((long long)u * kPairM + prow) * 2 + h;
+        for (int h = 0; h < parts; h++) {
+            const long long seg = ((long long)u * kPairM + prow) * parts + h;
             int c = candCount[seg];
             if (c > cap) {
                 overflow = 1;
@@ -423,14 +424,22 @@ SmemPlan planSmem(int KB) {
     return {ys, fixed + ys * stage};
 }
 
+// column parts per tile = epilogue warps / 4 (FB200_TC_PARTS: tuning knob, 2 or 4)
+int tcParts() {
+    static const int parts = getenv("FB200_TC_PARTS") ? atoi(getenv("FB200_TC_PARTS")) : 4;
+    return parts == 2 ? 2 : 4;
+}
+
 template <bool DUMP>
 void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
     // FB200_TC_DEBUG_SKIP=1 (timing experiments only): skip the filter, keep the TMEM loads
     static const bool dbg = getenv("FB200_TC_DEBUG_SKIP") && atoi(getenv("FB200_TC_DEBUG_SKIP")) != 0;
-    auto kern = dbg ? flat_tc_kernel<DUMP, 1> : flat_tc_kernel<DUMP, 0>;
+    const int parts = tcParts();
+    auto kern = parts == 2 ? (dbg ? flat_tc_kernel<DUMP, 1, 2> : flat_tc_kernel<DUMP, 0, 2>)
+                           : (dbg ? flat_tc_kernel<DUMP, 1, 4> : flat_tc_kernel<DUMP, 0, 4>);
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("flat_tc", stream);
-    kern<<<grid, kThreads, smem, stream>>>(mq, my, p);
+    kern<<<grid, tcThreads(parts), smem, stream>>>(mq, my, p);
     KernelTiming::end("flat_tc", stream);
     CUDA_CHECK_LAST();
 }
@@ -611,6 +620,7 @@ void runFlatTcSearch(
         struct Round {
             int begin, end, slices, tilesPerSlice, cap;
         };
+        const int parts = tcParts();
         std::vector<Round> rounds;
         {
             int64_t seen = 0;
@@ -644,9 +654,9 @@ void runFlatTcSearch(
                 int S = (int)ceil_div(tiles, tps);
                 int cap;
                 if (seen == 0) {
-                    cap = (int)(tps * (kTileN / 2)); // everything passes in round 0
+                    cap = (int)(tps * (kTileN / parts)); // everything passes in round 0
                 } else {
-                    double expect = 1.5 * k * ((double)tps / (double)seen) * 0.5;
+                    double expect = 1.5 * k * ((double)tps / (double)seen) / parts;
                     cap = next_pow2((int)std::min<double>(1 << 20, 4.0 * expect + 32.0));
                     cap = std::max(cap, 32);
                 }
@@ -657,8 +667,8 @@ void runFlatTcSearch(
         size_t arenaBytes = 0, countBytes = 0;
         for (auto& r : rounds) {
             size_t units = (size_t)qPairs * r.slices;
-            arenaBytes = std::max(arenaBytes, units * kSegsPerUnit * (size_t)r.cap * sizeof(uint2));
-            countBytes = std::max(countBytes, units * kSegsPerUnit * sizeof(int));
+            arenaBytes = std::max(arenaBytes, units * tcSegsPerUnit(parts) * (size_t)r.cap * sizeof(uint2));
+            countBytes = std::max(countBytes, units * tcSegsPerUnit(parts) * sizeof(int));
         }
         auto arena = res->temp(device, arenaBytes);
         auto counts = res->temp(device, countBytes);
@@ -696,6 +706,7 @@ void runFlatTcSearch(
                     k,
                     LIST,
                     r.slices,
+                    parts,
                     arena.as<uint2>(),
                     r.cap,
                     counts.as<int>(),

@@ -9,17 +9,17 @@
 //     shared memory feeds two MMA groups (accumulators h = 0, 1 -> the two 256-column halves of TMEM).
 //   * tcgen05.ld is not a limit (~770 B/cycle/SM measured), so fp32 accumulators are drained in full.
 //
-// Roles in one persistent CTA (320 threads, one CTA per SM):
+// Roles in one persistent CTA (64 + 128 * PARTS threads, one CTA per SM):
 //   warp 0   : TMA producer -- the unit's two query tiles once, then database tiles (256 rows x dpad
 //              fp16, 128B-swizzled K-major) through an mbarrier ring, plus a small ring with each
 //              tile's 256 biases and its tile id
 //   warp 1   : single-thread tcgen05.mma issuer (SS mode, M=128 N=256 K=16, fp32 accumulate in TMEM)
-//   warps 2-9: epilogue.  A thread owns one TMEM lane = one query row of each of the unit's two query
-//              tiles, and 128 of a tile's 256 columns.  It streams accumulators with tcgen05.ld in
-//              32-column chunks (software-pipelined against the filter), computes
-//              score = acc * inv + bias with FFMA2, folds 8 columns with FMNMX3 and compares against the
-//              query's threshold held in a register.  Survivors (rare) are appended with plain stores
-//              to a thread-private candidate segment; scores never reach HBM.
+//   warps 2+ : epilogue, 4 * PARTS warps.  A thread owns one TMEM lane = one query row of each of the
+//              unit's two query tiles, and 256 / PARTS of a tile's columns.  It drains its slice of an
+//              accumulator with tcgen05.ld (32 or 64 columns at a time), hands the accumulator back to
+//              the MMA warp after its last load, and computes score = acc * inv + bias with FFMA2, folds 8 columns with FMNMX3
+//              and compares against the query's threshold held in a register.  Survivors (rare) are
+//              appended with plain stores to a thread-private candidate segment; scores never reach HBM.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -34,12 +34,20 @@ constexpr int kTileM = 128;       // queries per MMA tile (TMEM lanes)
 constexpr int kPairM = 256;       // queries per work unit (two MMA tiles)
 constexpr int kTileN = 256;       // database rows per tile (TMEM columns per accumulator)
 constexpr int kKBlock = 64;       // fp16 elements per 128-byte swizzle row
-constexpr int kThreads = 320;
-constexpr int kEpiWarps = 8;
+// PARTS = column parts of a tile filtered by different warps: 4 * PARTS epilogue warps (a warp may only
+// touch its own TMEM lane quarter), 64 + 128 * PARTS threads per CTA.  With PARTS = 4 two schedulers
+// hold 5 warps, which caps a thread at 96 registers: the filter then works on 32-column chunks.
+// (Measured on B200, N=10M d=128 nq=10k: PARTS=2 / 64-column blocks 23.6 ms per step in this kernel,
+// PARTS=4 / 32-column chunks 20.9 ms, PARTS=4 / 64-column blocks with setmaxnreg 112 registers 23.2 ms.)
+constexpr int kMaxParts = 4;
 constexpr int kMaxYStages = 6;
 constexpr int kBiasSlots = 4;
-constexpr int kSegsPerUnit = 512; // 256 query rows x 2 column halves
-constexpr int kColsPerThread = kTileN / 2; // columns of a tile one epilogue thread filters
+__host__ __device__ constexpr int tcThreads(int parts) {
+    return 64 + 128 * parts; // TMA warp, MMA warp, 4 * parts epilogue warps
+}
+__host__ __device__ constexpr int tcSegsPerUnit(int parts) {
+    return kPairM * parts; // 256 query rows x column parts
+}
 
 struct TcParams {
     int numUnits;
@@ -184,8 +192,8 @@ __device__ __forceinline__ void epi_filter64(
     }
 }
 
-template <bool DUMP, int DBG>
-__global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
+template <bool DUMP, int DBG, int PARTS>
+__global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
         const __grid_constant__ CUtensorMap mapQ,
         const __grid_constant__ CUtensorMap mapY,
         const TcParams p) {
@@ -212,6 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int kEpiWarps = 4 * PARTS;
+    constexpr int kColsPerThread = kTileN / PARTS; // columns of a tile one epilogue thread filters
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&mapQ);
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
         // ================================ epilogue ================================
         const int ew = warp - 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // which 128 columns of a tile
+        const int half = ew >> 2;      // which column part of a tile
         const int row = quarter * 32 + lane;
         const float inv = *p.invScalePtr;
         const uint32_t lane_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerThread);
@@ -341,17 +351,19 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
             const int q1 = q0 + kTileM;
             const float thr0 = (!DUMP && q0 < p.nq) ? p.thr[q0] : CUDART_INF_F;
             const float thr1 = (!DUMP && q1 < p.nq) ? p.thr[q1] : CUDART_INF_F;
-            const long long seg0 = ((long long)u * kPairM + row) * 2 + half;
-            const long long seg1 = ((long long)u * kPairM + kTileM + row) * 2 + half;
+            const long long seg0 = ((long long)u * kPairM + row) * PARTS + half;
+            const long long seg1 = ((long long)u * kPairM + kTileM + row) * PARTS + half;
             uint2* buf0 = DUMP ? nullptr : p.cand + seg0 * p.cap;
             uint2* buf1 = DUMP ? nullptr : p.cand + seg1 * p.cap;
             int cnt0 = 0, cnt1 = 0;
             const int pb = p.tileBegin + sl * p.tilesPerSlice;
             const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
 
-            // Block stream per database tile: (h=0: blocks 0,1), (h=1: blocks 0,1), 64 columns each
-            // (two x32 TMEM loads), filtered together for instruction-level parallelism.
-            uint32_t a0[32], a1[32];
+            // PARTS == 2: block stream per database tile (h=0: blocks 0,1), (h=1: blocks 0,1), 64 columns each
+            // (two x32 TMEM loads) filtered together for instruction-level parallelism with 2 warps per
+            // scheduler.  PARTS == 4: 4 warps per scheduler hide the latencies; 32-column chunks keep the
+            // thread under the 112-register budget of a 576-thread CTA.
+            uint32_t a0[32], a1[PARTS == 2 ? 32 : 1];
             for (int pp = pb; pp < pe; pp++) {
                 ptx::mbar_wait(&b_full[bs], bphase);
                 const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
@@ -368,8 +380,12 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                     ptx::tc_fence_after();
 #pragma unroll 1
                     for (int blk = 0; blk < 2; blk++) {
-                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64), a0);
-                        ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64 + 32), a1);
+                        if constexpr (PARTS == 2) {
+                            ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64), a0);
+                            ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 64 + 32), a1);
+                        } else {
+                            ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(blk * 32), a0);
+                        }
                         ptx::tmem_ld_wait();
                         if (blk == 1) { // the accumulator is out of TMEM: hand it back to the MMA warp
                             ptx::tc_fence_before();
@@ -377,8 +393,12 @@ __global__ void __launch_bounds__(kThreads, 1) flat_tc_kernel(
                             if (lane == 0)
                                 ptx::mbar_arrive(&t_empty[h]);
                         }
-                        if (DBG == 0)
-                            epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, bp + blk * 256, buf, cnt);
+                        if (DBG == 0) {
+                            if constexpr (PARTS == 2)
+                                epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, bp + blk * 256, buf, cnt);
+                            else
+                                epi_filter32<DUMP>(p, a0, q, colBase + blk * 32, inv, thr, bp + blk * 128, buf, cnt);
+                        }
                     }
                     if (h)
                         cnt1 = cnt;

@@ -12,6 +12,7 @@
 //     LUT access is bank-conflict-free by construction (lane t reads bank (t + j) % 32).
 // LUT and distances never touch HBM; the running top-k stays in shared memory (select.cuh).
 #include <cfloat>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "select.cuh"
@@ -24,7 +25,6 @@ int ivfScanChunks(int device, int64_t nq, int nprobe, int* probesPerCta);
 
 namespace {
 
-constexpr int kWarps = 8;
 constexpr int kBuf = 64;
 constexpr int kLutSlots = 64; // 256 B per code value
 
@@ -80,7 +80,7 @@ __global__ void pq_list_from_interleaved_kernel(const uint8_t* __restrict__ src,
 
 // block-level merge of the per-warp lists into warp 0 + write-out.  List ids are arena positions;
 // the user labels are looked up only for the k survivors.
-template <typename IdT>
+template <typename IdT, int kWarps>
 __device__ void merge_and_write(
         WarpTopK<IdT>& w,
         int warp,
@@ -122,7 +122,7 @@ __device__ void merge_and_write(
 // live across the probes of the chunk, so the number of candidates that pass the threshold grows with
 // log(vectors scanned per CTA), not with the number of (query, probe) pairs; per probe only the LUT is
 // rebuilt.  Keys: L2 -> sum of LUT entries; IP -> -(q.centroid) - sum (coarse term folded in per probe).
-template <int M, bool IS_L2, typename IdT>
+template <int M, bool IS_L2, typename IdT, int kWarps, bool PREFETCH, int LU>
 __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
@@ -157,11 +157,37 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
     const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
     const unsigned lane4 = (unsigned)lane << 2;
 
+    // kU groups per iteration; the loads of iteration i+1 are issued before the lookups of iteration i
+    // (register double buffer), so each warp always has kU * 32 * M bytes of the HBM stream in flight
+    constexpr int kU = 4;
+    constexpr int kStride = kWarps * kU;
     const int pEnd = min(nprobe, (chunk + 1) * probesPerCta);
     for (int p = chunk * probesPerCta; p < pEnd; p++) {
         const idx_t l = probes[(int64_t)q * nprobe + p];
         if (l < 0)
             continue; // block-uniform
+        const int len = listLen[l];
+        const int64_t ls = listStart[l];
+        const uint8_t* codes = arenaCodes + ls * (int64_t)M;
+        const int ngroups = (len + 31) >> 5;
+        if (ngroups == 0)
+            continue;
+        auto load = [&](uint4(&buf)[kU][M / 16], int g0) {
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
+                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+#pragma unroll
+                for (int h = 0; h < M / 16; h++)
+                    buf[u][h] = __ldg(gp + h * 32);
+            }
+        };
+        // this warp's first iteration of the list is requested before the LUT is (re)built: the HBM
+        // latency hides behind the build
+        uint4 cur[kU][M / 16], nxt[kU][M / 16];
+        int g0 = warp * kU;
+        if (PREFETCH && g0 < ngroups)
+            load(cur, g0);
         __syncthreads(); // every warp is done with the previous probe's LUT
         for (int i = threadIdx.x; i < d; i += blockDim.x) {
             float v = Q[(int64_t)q * d + i];
@@ -169,7 +195,8 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         }
         __syncthreads();
         // ---- LUT: entry (c, m) -> slots m, m+M, ... (< 64).  e = c*M + m: coalesced pqT reads, conflict-free writes
-        for (int e = threadIdx.x; e < 256 * M; e += blockDim.x) {
+#pragma unroll LU
+        for (int e = threadIdx.x; e < 256 * M; e += kWarps * 32) {
             const int c = e / M, m = e - c * M;
             const float* cp = pqT + (size_t)e * dsub;
             const float* rp = rs + m * dsub;
@@ -208,30 +235,20 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         }
         __syncthreads();
 
-        const int len = listLen[l];
-        const int64_t ls = listStart[l];
-        const uint8_t* codes = arenaCodes + ls * (int64_t)M;
         const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
-        const int ngroups = (len + 31) >> 5;
-        // kU groups per iteration: all of a lane's 128-bit loads are issued before the first lookup, so each
-        // warp keeps kU * M/16 * 512 B in flight (memory-level parallelism for the HBM stream)
-        constexpr int kU = 4;
-        for (int g0 = warp * kU; g0 < ngroups; g0 += kWarps * kU) {
-            uint4 c4[kU][M / 16];
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
-                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-#pragma unroll
-                for (int h = 0; h < M / 16; h++)
-                    c4[u][h] = __ldg(gp + h * 32);
+        for (; g0 < ngroups; g0 += kStride) {
+            if (PREFETCH) {
+                if (g0 + kStride < ngroups)
+                    load(nxt, g0 + kStride);
+            } else {
+                load(cur, g0);
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                 for (int h = 0; h < M / 16; h++) {
-                    const unsigned wds[4] = {c4[u][h].x, c4[u][h].y, c4[u][h].z, c4[u][h].w};
+                    const unsigned wds[4] = {cur[u][h].x, cur[u][h].y, cur[u][h].z, cur[u][h].w};
 #pragma unroll
                     for (int wi = 0; wi < 4; wi++) {
 #pragma unroll
@@ -251,9 +268,16 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
                 const float key = IS_L2 ? a0 + a1 : (a0 + a1) + add;
                 w.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
             }
+            if (PREFETCH) {
+#pragma unroll
+                for (int u = 0; u < kU; u++)
+#pragma unroll
+                    for (int h = 0; h < M / 16; h++)
+                        cur[u][h] = nxt[u][h];
+            }
         }
     }
-    merge_and_write<IdT>(w, warp, lists, perWarp, LIST, k, arenaIds, oD, oI);
+    merge_and_write<IdT, kWarps>(w, warp, lists, perWarp, LIST, k, arenaIds, oD, oI);
 }
 
 } // namespace
@@ -291,8 +315,8 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2, typename IdT>
-static void launchScan(
+template <int M, bool IS_L2, typename IdT, int kWarps, bool PREFETCH, int LU>
+static void launchScanV(
         dim3 grid,
         size_t smem,
         cudaStream_t stream,
@@ -312,7 +336,7 @@ static void launchScan(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT, kWarps, PREFETCH, LU>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
@@ -320,6 +344,37 @@ static void launchScan(
             partI);
     KernelTiming::end("ivfpq_scan", stream);
     CUDA_CHECK_LAST();
+}
+
+// tuning variant (FB200_PQ_VARIANT): warps per CTA / register prefetch / LUT-build unroll
+//   0 = 16 warps, unroll 8 (default)   1 = 16 warps, unroll 1   2 = 16 warps, unroll 2
+//   3 = 8 warps, unroll 1              4 = 8 warps + register prefetch, unroll 1
+static int pqVariant() {
+    const char* e = getenv("FB200_PQ_VARIANT");
+    return e ? atoi(e) : 0;
+}
+static int pqVariantWarps(int v) {
+    return v >= 3 ? 8 : 16;
+}
+
+template <int M, bool IS_L2, typename IdT, typename... Args>
+static void launchScan(int variant, Args... args) {
+    switch (variant) {
+        case 1:
+            launchScanV<M, IS_L2, IdT, 16, false, 1>(args...);
+            break;
+        case 2:
+            launchScanV<M, IS_L2, IdT, 16, false, 2>(args...);
+            break;
+        case 3:
+            launchScanV<M, IS_L2, IdT, 8, false, 1>(args...);
+            break;
+        case 4:
+            launchScanV<M, IS_L2, IdT, 8, true, 1>(args...);
+            break;
+        default:
+            launchScanV<M, IS_L2, IdT, 16, false, 8>(args...);
+    }
 }
 
 void runIvfPqScanInterleaved(
@@ -350,7 +405,8 @@ void runIvfPqScanInterleaved(
     const int LIST = std::max(64, next_pow2(k));
     const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
     const size_t listBytes = wide ? SmemTopK<long long>::bytes(LIST, kBuf) : SmemTopK<int>::bytes(LIST, kBuf);
-    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * kWarps;
+    const int variant = pqVariant();
+    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * pqVariantWarps(variant);
     FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
     const bool l2 = metric == METRIC_L2;
     int probesPerCta = 1;
@@ -363,7 +419,7 @@ void runIvfPqScanInterleaved(
         dim3 grid((unsigned)chunks, (unsigned)nb);
 #define SCAN(M_, L2_, ID_)                                                                                         \
     launchScan<M_, L2_, ID_>(                                                                                      \
-            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
+            variant, grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
             coarseCentroids, pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(),   \
             partI.as<idx_t>())
 #define SCAN_ID(M_, L2_)        \
