@@ -354,6 +354,16 @@ def main():
                 "peak_source": "%s bf16 GEMM peak (sustained; kernel timed inside a multi-step loop), MEASURED_PEAKS.json" % pk_src,
                 "kernel": "flat_tc_kernel (tcgen05 fp16 scoring + fused top-k filter), %d launches/step" % (tc_n.value // steps if tc_n.value else 0),
                 "algorithmic_flops_per_step": flops_step}
+        # DRAM bytes per launch of this kernel, from the committed `ncu --set full` capture of this same
+        # workload (profiles/flat_tc_traffic.json, written by scripts/ncu_traffic.py); single GPU only
+        tpath = os.path.join(ROOT, "profiles", "flat_tc_traffic.json")
+        if world == 1 and N_TOTAL == 10_000_000 and os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                roof["traffic"] = tj["dram_bytes_per_launch"]
+                roof["traffic_source"] = tj["source"]
+            except Exception:
+                pass
         if tc_ms_step:
             roof["achieved"] = flops_step / (tc_ms_step * 1e-3) / 1e12
             roof["frac"] = roof["achieved"] / peak_tf

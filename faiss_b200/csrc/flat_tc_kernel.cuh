@@ -11,14 +11,12 @@
 //
 // Roles in one persistent CTA (64 + 128 * PARTS threads, one CTA per SM):
 //   warp 0   : TMA producer -- the unit's two query tiles once, then database tiles (256 rows x dpad
-//              fp16, 128B-swizzled K-major) through an mbarrier ring, plus a small ring with each
-//              tile's 256 biases and its tile id
+//              fp16, 128B-swizzled K-major) through an mbarrier ring
 //   warp 1   : single-thread tcgen05.mma issuer (SS mode, M=128 N=256 K=16, fp32 accumulate in TMEM)
 //   warps 2+ : epilogue, 4 * PARTS warps.  A thread owns one TMEM lane = one query row of each of the
 //              unit's two query tiles, and 256 / PARTS of a tile's columns.  It drains its slice of an
 //              accumulator with tcgen05.ld (32 or 64 columns at a time), hands the accumulator back to
-//              the MMA warp after its last load, and computes score = acc * inv + bias with FFMA2, folds 8 columns with FMNMX3
-//              and compares against the query's threshold held in a register.  Survivors (rare) are
+//              the MMA warp after its last load, and filters (below).  Survivors (rare) are
 //              appended with plain stores to a thread-private candidate segment; scores never reach HBM.
 #pragma once
 
@@ -41,7 +39,6 @@ constexpr int kKBlock = 64;       // fp16 elements per 128-byte swizzle row
 // PARTS=4 / 32-column chunks 20.9 ms, PARTS=4 / 64-column blocks with setmaxnreg 112 registers 23.2 ms.)
 constexpr int kMaxParts = 4;
 constexpr int kMaxYStages = 6;
-constexpr int kBiasSlots = 4;
 __host__ __device__ constexpr int tcThreads(int parts) {
     return 64 + 128 * parts; // TMA warp, MMA warp, 4 * parts epilogue warps
 }
@@ -60,7 +57,8 @@ struct TcParams {
     int KB;             // dpad / 64
     int yStages;
     const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
-    const float* bias;  // [numTiles*256], -inf padded
+    const float* bias;  // [numTiles*256], -inf padded (read on the slow path only)
+    const float* tileMaxBias; // [numTiles] max bias of the tile's rows (rows are stored sorted by norm)
     const float* thr;   // [nq]  pass if score > thr
     uint2* cand;        // [numUnits*512][cap] (score bits, row)
     int cap;
@@ -74,17 +72,23 @@ __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
     return (int)(((unsigned long long)pos * p.permA + p.permB) % p.numTiles);
 }
 
-// Filter 32 columns of one query row: score = acc * inv + bias; one maximum per 8 columns against the
-// query's threshold; the rare survivors are appended to the thread-private candidate segment.
+// Filter of one query row against a run of columns (database rows).
+//
+// The exact test is  score = fma(acc, inv, bias[row]) > thr.  The database tiles hold rows SORTED BY
+// NORM, so the biases of a tile are nearly equal and  bound = fma(max acc, inv, max bias of the tile)
+// is a tight upper bound of every score in a group (inv > 0 and rounding are monotonic: no false
+// negatives, bit for bit).  The fast path is therefore a pure FMNMX3 tree over raw accumulators --
+// no bias loads, no per-element FMA -- plus one FMA per 32 columns; the rare group whose bound beats
+// the threshold evaluates the exact test with biases read through L1/L2.
 template <bool DUMP>
 __device__ __forceinline__ void epi_filter32(
         const TcParams& p,
         const uint32_t (&r)[32],
         int q,
-        long long colBase, // global row index of column 0 of this chunk
+        long long colBase, // global (sorted) row index of column 0 of this chunk
         float inv,
         float thr,
-        uint32_t bp, // shared address of the 32 biases
+        float maxb,
         uint2* buf,
         int& cnt) {
     if (DUMP) {
@@ -96,31 +100,27 @@ __device__ __forceinline__ void epi_filter32(
         }
         return;
     }
-    float v[32];
     float mg[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const float4 b0 = ptx::lds128(bp + (2 * g) * 16);
-        const float4 b1 = ptx::lds128(bp + (2 * g + 1) * 16);
         const int o = 8 * g;
-        ptx::fma2(v[o + 0], v[o + 1], __uint_as_float(r[o + 0]), __uint_as_float(r[o + 1]), inv, b0.x, b0.y);
-        ptx::fma2(v[o + 2], v[o + 3], __uint_as_float(r[o + 2]), __uint_as_float(r[o + 3]), inv, b0.z, b0.w);
-        ptx::fma2(v[o + 4], v[o + 5], __uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]), inv, b1.x, b1.y);
-        ptx::fma2(v[o + 6], v[o + 7], __uint_as_float(r[o + 6]), __uint_as_float(r[o + 7]), inv, b1.z, b1.w);
-        const float a = ptx::max3(v[o + 0], v[o + 1], v[o + 2]);
-        const float c = ptx::max3(v[o + 3], v[o + 4], v[o + 5]);
-        mg[g] = ptx::max3(a, c, fmaxf(v[o + 6], v[o + 7]));
+        const float a = ptx::max3(__uint_as_float(r[o + 0]), __uint_as_float(r[o + 1]), __uint_as_float(r[o + 2]));
+        const float c = ptx::max3(__uint_as_float(r[o + 3]), __uint_as_float(r[o + 4]), __uint_as_float(r[o + 5]));
+        mg[g] = ptx::max3(a, c, fmaxf(__uint_as_float(r[o + 6]), __uint_as_float(r[o + 7])));
     }
-    if (ptx::max3(mg[0], mg[1], fmaxf(mg[2], mg[3])) > thr) {
+    const float m = ptx::max3(mg[0], mg[1], fmaxf(mg[2], mg[3]));
+    if (fmaf(m, inv, maxb) > thr) {
+        const float* bias = p.bias + colBase;
         const unsigned rowBase = (unsigned)colBase;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            if (mg[g] > thr) {
+            if (fmaf(mg[g], inv, maxb) > thr) {
 #pragma unroll
                 for (int j = 8 * g; j < 8 * g + 8; j++) {
-                    if (v[j] > thr) {
+                    const float v = fmaf(__uint_as_float(r[j]), inv, __ldg(bias + j));
+                    if (v > thr) {
                         if (cnt < p.cap)
-                            buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
+                            buf[cnt] = make_uint2(__float_as_uint(v), rowBase + j);
                         cnt++;
                     }
                 }
@@ -129,8 +129,8 @@ __device__ __forceinline__ void epi_filter32(
     }
 }
 
-// 64 columns at once (two 32-column register sets): twice the independent work per warp, which the
-// two-warps-per-scheduler epilogue needs to cover its fixed-latency dependency stalls.
+// 64 columns (two 32-column register sets) in one go: more independent work per warp for the
+// two-warps-per-scheduler configuration (PARTS = 2).
 template <bool DUMP>
 __device__ __forceinline__ void epi_filter64(
         const TcParams& p,
@@ -140,56 +140,11 @@ __device__ __forceinline__ void epi_filter64(
         long long colBase,
         float inv,
         float thr,
-        uint32_t bp,
+        float maxb,
         uint2* buf,
         int& cnt) {
-    if (DUMP) {
-        epi_filter32<true>(p, r0, q, colBase, inv, thr, bp, buf, cnt);
-        epi_filter32<true>(p, r1, q, colBase + 32, inv, thr, bp + 128, buf, cnt);
-        return;
-    }
-    float v[64];
-    float mg[8];
-    // two independent 8-column groups per step (one from each register set), biases loaded just in time
-#pragma unroll
-    for (int gg = 0; gg < 4; gg++) {
-        const float4 x0 = ptx::lds128(bp + (2 * gg) * 16);
-        const float4 x1 = ptx::lds128(bp + (2 * gg + 1) * 16);
-        const float4 y0 = ptx::lds128(bp + 128 + (2 * gg) * 16);
-        const float4 y1 = ptx::lds128(bp + 128 + (2 * gg + 1) * 16);
-        const int o = 8 * gg;
-        ptx::fma2(v[o + 0], v[o + 1], __uint_as_float(r0[o + 0]), __uint_as_float(r0[o + 1]), inv, x0.x, x0.y);
-        ptx::fma2(v[32 + o + 0], v[32 + o + 1], __uint_as_float(r1[o + 0]), __uint_as_float(r1[o + 1]), inv, y0.x, y0.y);
-        ptx::fma2(v[o + 2], v[o + 3], __uint_as_float(r0[o + 2]), __uint_as_float(r0[o + 3]), inv, x0.z, x0.w);
-        ptx::fma2(v[32 + o + 2], v[32 + o + 3], __uint_as_float(r1[o + 2]), __uint_as_float(r1[o + 3]), inv, y0.z, y0.w);
-        ptx::fma2(v[o + 4], v[o + 5], __uint_as_float(r0[o + 4]), __uint_as_float(r0[o + 5]), inv, x1.x, x1.y);
-        ptx::fma2(v[32 + o + 4], v[32 + o + 5], __uint_as_float(r1[o + 4]), __uint_as_float(r1[o + 5]), inv, y1.x, y1.y);
-        ptx::fma2(v[o + 6], v[o + 7], __uint_as_float(r0[o + 6]), __uint_as_float(r0[o + 7]), inv, x1.z, x1.w);
-        ptx::fma2(v[32 + o + 6], v[32 + o + 7], __uint_as_float(r1[o + 6]), __uint_as_float(r1[o + 7]), inv, y1.z, y1.w);
-        const float a = ptx::max3(v[o + 0], v[o + 1], v[o + 2]);
-        const float e = ptx::max3(v[32 + o + 0], v[32 + o + 1], v[32 + o + 2]);
-        const float c = ptx::max3(v[o + 3], v[o + 4], v[o + 5]);
-        const float f = ptx::max3(v[32 + o + 3], v[32 + o + 4], v[32 + o + 5]);
-        mg[gg] = ptx::max3(a, c, fmaxf(v[o + 6], v[o + 7]));
-        mg[4 + gg] = ptx::max3(e, f, fmaxf(v[32 + o + 6], v[32 + o + 7]));
-    }
-    const float m = fmaxf(ptx::max3(mg[0], mg[1], mg[2]), fmaxf(ptx::max3(mg[3], mg[4], mg[5]), fmaxf(mg[6], mg[7])));
-    if (m > thr) {
-        const unsigned rowBase = (unsigned)colBase;
-#pragma unroll
-        for (int g = 0; g < 8; g++) {
-            if (mg[g] > thr) {
-#pragma unroll
-                for (int j = 8 * g; j < 8 * g + 8; j++) {
-                    if (v[j] > thr) {
-                        if (cnt < p.cap)
-                            buf[cnt] = make_uint2(__float_as_uint(v[j]), rowBase + j);
-                        cnt++;
-                    }
-                }
-            }
-        }
-    }
+    epi_filter32<DUMP>(p, r0, q, colBase, inv, thr, maxb, buf, cnt);
+    epi_filter32<DUMP>(p, r1, q, colBase + 32, inv, thr, maxb, buf, cnt);
 }
 
 template <bool DUMP, int DBG, int PARTS>
@@ -212,11 +167,7 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
     uint64_t* y_empty = y_full + kMaxYStages;
     uint64_t* t_full = y_empty + kMaxYStages; // [2] one per accumulator half
     uint64_t* t_empty = t_full + 2;
-    uint64_t* b_full = t_empty + 2;
-    uint64_t* b_empty = b_full + kBiasSlots;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kBiasSlots);
-    int* tileS = reinterpret_cast<int*>(tmem_slot + 2);                // [kBiasSlots]
-    float* biasS = reinterpret_cast<float*>(tileS + kBiasSlots + 2);   // [kBiasSlots][256], 16B aligned
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -236,10 +187,6 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
             ptx::mbar_init(&t_full[i], 1);
             ptx::mbar_init(&t_empty[i], kEpiWarps);
         }
-        for (int i = 0; i < kBiasSlots; i++) {
-            ptx::mbar_init(&b_full[i], 1);
-            ptx::mbar_init(&b_empty[i], kEpiWarps);
-        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -253,8 +200,8 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int ys = 0, bs = 0;
-            uint32_t yphase = 0, bphase = 0;
+            int ys = 0;
+            uint32_t yphase = 0;
             int it = 0;
             for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x, it++) {
                 const int pair = u % p.qPairs;
@@ -273,15 +220,6 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                     if (++ys == p.yStages) {
                         ys = 0;
                         yphase ^= 1;
-                    }
-                    // per-tile bias + tile id for the epilogue
-                    ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-                    ptx::sts32(ptx::smem_u32(tileS + bs), t);
-                    ptx::mbar_arrive_expect_tx(&b_full[bs], kTileN * 4);
-                    ptx::bulk_load_1d(biasS + bs * kTileN, p.bias + (long long)t * kTileN, kTileN * 4, &b_full[bs]);
-                    if (++bs == kBiasSlots) {
-                        bs = 0;
-                        bphase ^= 1;
                     }
                 }
             }
@@ -341,8 +279,8 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
         const int row = quarter * 32 + lane;
         const float inv = *p.invScalePtr;
         const uint32_t lane_acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kColsPerThread);
-        int bs = 0;
-        uint32_t bphase = 0, tphase = 0;
+        uint32_t tphase = 0;
+        const int permStep = (int)(p.permA % p.numTiles);
         for (int u = blockIdx.x; u < p.numUnits; u += gridDim.x) {
             const int pair = u % p.qPairs;
             const int sl = u / p.qPairs;
@@ -364,11 +302,18 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
             // scheduler.  PARTS == 4: 4 warps per scheduler hide the latencies; 32-column chunks keep the
             // thread under the 112-register budget of a 576-thread CTA.
             uint32_t a0[32], a1[PARTS == 2 ? 32 : 1];
+            // tile ids follow the producer's affine permutation incrementally; the tile's bias bound is
+            // fetched one tile ahead (its L2 latency would otherwise sit on the filter's critical path)
+            int t = pb < pe ? perm_tile(p, pb) : 0;
+            float maxbNext = (!DUMP && pb < pe) ? __ldg(p.tileMaxBias + t) : 0.f;
             for (int pp = pb; pp < pe; pp++) {
-                ptx::mbar_wait(&b_full[bs], bphase);
-                const int t = ptx::lds32(ptx::smem_u32(tileS + bs));
                 const long long colBase = (long long)t * kTileN + half * kColsPerThread;
-                const uint32_t bp = ptx::smem_u32(biasS + bs * kTileN + half * kColsPerThread);
+                const float maxb = maxbNext;
+                t += permStep;
+                if (t >= (int)p.numTiles)
+                    t -= (int)p.numTiles;
+                if (!DUMP && pp + 1 < pe)
+                    maxbNext = __ldg(p.tileMaxBias + t);
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const int q = h ? q1 : q0;
@@ -395,9 +340,9 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                         }
                         if (DBG == 0) {
                             if constexpr (PARTS == 2)
-                                epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, bp + blk * 256, buf, cnt);
+                                epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, maxb, buf, cnt);
                             else
-                                epi_filter32<DUMP>(p, a0, q, colBase + blk * 32, inv, thr, bp + blk * 128, buf, cnt);
+                                epi_filter32<DUMP>(p, a0, q, colBase + blk * 32, inv, thr, maxb, buf, cnt);
                         }
                     }
                     if (h)
@@ -406,13 +351,6 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                         cnt0 = cnt;
                 }
                 tphase ^= 1;
-                __syncwarp();
-                if (lane == 0)
-                    ptx::mbar_arrive(&b_empty[bs]);
-                if (++bs == kBiasSlots) {
-                    bs = 0;
-                    bphase ^= 1;
-                }
             }
             if (!DUMP) {
                 p.candCount[seg0] = cnt0;

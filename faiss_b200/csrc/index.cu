@@ -278,7 +278,9 @@ GpuIndexFlat::GpuIndexFlat(
           flatConfig_(config),
           vecs_(resources_.get(), config.device, AllocType::FlatData),
           y16_(resources_.get(), config.device, AllocType::FlatData),
-          bias_(resources_.get(), config.device, AllocType::FlatData) {
+          bias_(resources_.get(), config.device, AllocType::FlatData),
+          perm_(resources_.get(), config.device, AllocType::FlatData),
+          tileMaxBias_(resources_.get(), config.device, AllocType::FlatData) {
     this->is_trained = true;
     dpad_ = (int)round_up(dims, 64);
 }
@@ -290,6 +292,8 @@ void GpuIndexFlat::reset() {
     vecs_.clear();
     y16_.clear();
     bias_.clear();
+    perm_.clear();
+    tileMaxBias_.clear();
     tcDirty_ = true;
     this->ntotal = 0;
 }
@@ -333,6 +337,12 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
     const int64_t padRows = round_up(n, 256) + 256; // whole 256-row tiles, -inf beyond n
     y16_.resize((size_t)n * dpad_, stream);
     bias_.resize((size_t)padRows, stream);
+    tileMaxBias_.resize((size_t)(padRows / 256), stream);
+    const bool sorted = metric_type == METRIC_L2; // IP has no bias: row order is kept
+    if (sorted)
+        perm_.resize((size_t)n, stream);
+    else
+        perm_.clear();
     auto scal = resources_->temp(config_.device, sizeof(float) * 2);
     auto norms = resources_->temp(config_.device, sizeof(float) * n);
     CUDA_VERIFY(cudaMemsetAsync(scal.data, 0, sizeof(float) * 2, stream));
@@ -348,7 +358,9 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
     }
     fill_float_kernel<<<(unsigned)ceil_div(padRows, 256), 256, 0, stream>>>(bias_.data(), padRows, -INFINITY);
     CUDA_CHECK_LAST();
-    runFlatTcPrepareRows(vecs_.data(), n, d, dpad_, scale, metric_type, y16_.data(), bias_.data(), norms.as<float>(), stream);
+    runFlatTcPrepareRows(
+            resources_.get(), config_.device, vecs_.data(), n, d, dpad_, scale, metric_type, y16_.data(), bias_.data(),
+            sorted ? perm_.data() : nullptr, tileMaxBias_.data(), norms.as<float>(), stream);
     runMaxOf(norms.as<float>(), n, scal.as<float>() + 1, stream);
     CUDA_VERIFY(cudaMemcpyAsync(h, scal.data, sizeof(float) * 2, cudaMemcpyDeviceToHost, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
@@ -375,7 +387,8 @@ void GpuIndexFlat::searchImpl_(idx_t n, const float* xDev, int k, float* dDev, i
     if (tc) {
         prepareTensorCoreData_();
         runFlatTcSearch(
-                resources_.get(), config_.device, xDev, n, vecs_.data(), y16_.data(), bias_.data(), yScale_,
+                resources_.get(), config_.device, xDev, n, vecs_.data(), y16_.data(), bias_.data(),
+                metric_type == METRIC_L2 ? perm_.data() : nullptr, tileMaxBias_.data(), yScale_,
                 yMaxNorm_, this->ntotal, d, dpad_, k, metric_type, dDev, iDev, stream);
         lastSearchUsedTensorCores = 1;
         lastSearchFallbackQueries = lastFlatTcFallbacks();

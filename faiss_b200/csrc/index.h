@@ -228,6 +228,8 @@ class GpuIndexFlat : public GpuIndex {
     // tensor-core side data, rebuilt lazily after adds
     mutable DeviceVector<__half> y16_;
     mutable DeviceVector<float> bias_;
+    mutable DeviceVector<int> perm_;          // L2: stored (norm-sorted) position -> row id
+    mutable DeviceVector<float> tileMaxBias_; // max bias per 256-row tile
     mutable bool tcDirty_ = true;
     mutable float yScale_ = 1.f;
     mutable float yMaxNorm_ = 0.f;

@@ -80,9 +80,12 @@ void runGatherRows(const float* src, const idx_t* ids, int64_t n, int d, float* 
 // ---------------------------------------------------------------- flat_tc.cu  (tcgen05 path)
 struct FlatTcPlan; // opaque: tensor maps + scratch sizing for one (index, nq, k) shape
 
-// fp32 rows -> scaled fp16 rows (padded to dpad, multiple of 64) + score bias; incremental (rows
-// [n0, n0+n) only).  bias[j] = -||y_j||^2/2 for L2, 0 for IP.
+// fp32 rows -> scaled fp16 rows (padded to dpad, multiple of 64) + score bias (bias = -||y||^2/2 for
+// L2, 0 for IP) + per-256-row-tile maximum bias.  With perm != null (L2) the fp16 copy is stored in
+// order of increasing norm: perm[stored position] = row id.  norms[] stays in row order.
 void runFlatTcPrepareRows(
+        GpuResources* res,
+        int device,
         const float* Y,
         int64_t n,
         int d,
@@ -91,6 +94,8 @@ void runFlatTcPrepareRows(
         MetricType metric,
         __half* Y16,
         float* bias,
+        int* perm,
+        float* tileMaxBias,
         float* norms,
         cudaStream_t stream);
 
@@ -109,8 +114,10 @@ void runFlatTcSearch(
         const float* Q,
         int64_t nq,
         const float* Y,      // fp32 rows [n,d] (exact re-rank)
-        const __half* Y16,   // fp16 scaled rows [n,dpad]
-        const float* bias,   // [n]
+        const __half* Y16,   // fp16 scaled rows [n,dpad], stored order
+        const float* bias,   // [n] stored order
+        const int* perm,     // stored position -> row id (null: identity)
+        const float* tileMaxBias, // [ceil(n/256)]
         float yScale,        // power of two applied to Y16
         float yMaxNorm,      // max ||y|| (unscaled)
         int64_t n,
