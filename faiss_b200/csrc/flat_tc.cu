@@ -168,6 +168,10 @@ __global__ void tc_prepare_queries_kernel(
     }
 }
 
+// pending-candidate buffer of the select kernel: a round brings ~(growth-1)*k candidates per query, and
+// the cost of a flush is dominated by the merge into the 2k-entry list -- fewer, larger flushes
+constexpr int kSelectBuf = 128;
+
 // Fold this round's candidate segments into the per-query base list; set the new threshold.
 //   base lists hold (key = -score, id = row) sorted ascending; sentinel = (+inf, INT_MAX)
 __global__ void tc_select_kernel(
@@ -190,7 +194,7 @@ __global__ void tc_select_kernel(
     const int q = blockIdx.x * (blockDim.x >> 5) + warp;
     if (q >= nq)
         return;
-    constexpr int BUF = 64;
+    constexpr int BUF = kSelectBuf;
     unsigned char* base = smem_raw + SmemTopK<int>::bytes(LIST, BUF) * warp;
     WarpTopK<int> w;
     w.init(reinterpret_cast<float*>(base), reinterpret_cast<int*>(base + sizeof(float) * (LIST + BUF)), LIST, BUF, LIST);
@@ -304,6 +308,8 @@ __global__ void tc_rerank_kernel(
             // canonical order: sequential FMA over the dimension (loads vectorised, math not reordered)
             int i = 0;
             if ((d & 3) == 0) {
+                // unrolled: 8 independent 16-byte row loads in flight per lane (the FMA chain stays sequential)
+#pragma unroll 8
                 for (; i < d; i += 4) {
                     const float4 a4 = *reinterpret_cast<const float4*>(qp + i);
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(yp + i));
@@ -737,8 +743,8 @@ void runFlatTcSearch(
         auto arena = res->temp(device, arenaBytes);
         auto counts = res->temp(device, countBytes);
 
-        const int selWarps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / SmemTopK<int>::bytes(LIST, 64)));
-        const size_t selSmem = SmemTopK<int>::bytes(LIST, 64) * selWarps;
+        const int selWarps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / SmemTopK<int>::bytes(LIST, kSelectBuf)));
+        const size_t selSmem = SmemTopK<int>::bytes(LIST, kSelectBuf) * selWarps;
         CUDA_VERIFY(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)selSmem));
 
         for (auto& r : rounds) {

@@ -95,7 +95,8 @@ struct SmemTopK {
         for (int size = 2; size <= n; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int t = lane; t < (n >> 1); t += 32) {
-                    int a = 2 * stride * (t / stride) + (t % stride);
+                    // stride is a power of two: a = 2*stride*(t/stride) + t%stride without the division
+                    int a = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
                     int b = a + stride;
                     bool asc = ((a & size) == 0);
                     float ka = bk[a], kb = bk[b];
@@ -125,7 +126,7 @@ struct SmemTopK {
         // L is now bitonic and holds the LIST best; finish with a bitonic merge
         for (int stride = LIST >> 1; stride > 0; stride >>= 1) {
             for (int t = lane; t < (LIST >> 1); t += 32) {
-                int a = 2 * stride * (t / stride) + (t % stride);
+                int a = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
                 int b = a + stride;
                 float ka = keys[a], kb = keys[b];
                 IdT ia = ids[a], ib = ids[b];
