@@ -40,7 +40,6 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ntrain", type=int, default=1 << 20)
-    ap.add_argument("--variants", default=None, help="tuning: comma list of FB200_PQ_VARIANT values to time before the bench")
     args = ap.parse_args()
     N = args.n or (100_000_000 if args.index == "ivfpq" else 10_000_000)
     nprobe = args.nprobe or (32 if args.index == "ivfpq" else 64)
@@ -95,18 +94,6 @@ def main():
 
     lens = np.array([index.getListLength(l) for l in range(args.nlist)], dtype=np.int64)
 
-    if args.variants:
-        for v in args.variants.split(","):
-            os.environ["FB200_PQ_VARIANT"] = v
-            for _ in range(2):
-                index.search(xq, k)
-            torch.cuda.synchronize()
-            t0 = time.time()
-            for _ in range(3):
-                index.search(xq, k)
-            torch.cuda.synchronize()
-            log("variant %s: %.2f ms/step" % (v, (time.time() - t0) / 3 * 1e3))
-        os.environ.pop("FB200_PQ_VARIANT")
     for _ in range(max(3, args.warmup)):
         D, I = index.search(xq, k)
     torch.cuda.synchronize()

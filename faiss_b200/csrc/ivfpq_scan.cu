@@ -122,7 +122,7 @@ __device__ void merge_and_write(
 // live across the probes of the chunk, so the number of candidates that pass the threshold grows with
 // log(vectors scanned per CTA), not with the number of (query, probe) pairs; per probe only the LUT is
 // rebuilt.  Keys: L2 -> sum of LUT entries; IP -> -(q.centroid) - sum (coarse term folded in per probe).
-template <int M, bool IS_L2, typename IdT, int kWarps, bool PREFETCH, int LU>
+template <int M, bool IS_L2, typename IdT, int kWarps, int LU>
 __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
@@ -157,8 +157,10 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
     const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
     const unsigned lane4 = (unsigned)lane << 2;
 
-    // kU groups per iteration; the loads of iteration i+1 are issued before the lookups of iteration i
-    // (register double buffer), so each warp always has kU * 32 * M bytes of the HBM stream in flight
+    // kU groups (kU * 32 * M bytes) per warp iteration, all 128-bit loads issued before the first lookup;
+    // groups are dealt to the warps round-robin.  (Measured alternatives that did NOT help on B200, N=100M:
+    // a register double buffer for the next iteration's codes, 71 vs 66 ms; claiming groups from a shared
+    // counter to balance the per-probe barrier, 59.2 vs 57.7 ms; prefetch.global.L2 of the next chunk, 60.1.)
     constexpr int kU = 4;
     constexpr int kStride = kWarps * kU;
     const int pEnd = min(nprobe, (chunk + 1) * probesPerCta);
@@ -172,23 +174,7 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         const int ngroups = (len + 31) >> 5;
         if (ngroups == 0)
             continue;
-        auto load = [&](uint4(&buf)[kU][M / 16], int g0) {
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
-                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-#pragma unroll
-                for (int h = 0; h < M / 16; h++)
-                    buf[u][h] = __ldg(gp + h * 32);
-            }
-        };
-        // this warp's first iteration of the list is requested before the LUT is (re)built: the HBM
-        // latency hides behind the build
-        uint4 cur[kU][M / 16], nxt[kU][M / 16];
-        int g0 = warp * kU;
-        if (PREFETCH && g0 < ngroups)
-            load(cur, g0);
-        __syncthreads(); // every warp is done with the previous probe's LUT
+        __syncthreads(); // every warp is done with the previous probe's LUT (and its last claim)
         for (int i = threadIdx.x; i < d; i += blockDim.x) {
             float v = Q[(int64_t)q * d + i];
             rs[i] = IS_L2 ? v - coarse[l * d + i] : v;
@@ -236,12 +222,15 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         __syncthreads();
 
         const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
-        for (; g0 < ngroups; g0 += kStride) {
-            if (PREFETCH) {
-                if (g0 + kStride < ngroups)
-                    load(nxt, g0 + kStride);
-            } else {
-                load(cur, g0);
+        for (int g0 = warp * kU; g0 < ngroups; g0 += kStride) {
+            uint4 cur[kU][M / 16];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
+                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+#pragma unroll
+                for (int h = 0; h < M / 16; h++)
+                    cur[u][h] = __ldg(gp + h * 32);
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
@@ -267,13 +256,6 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
                 const int v = (g0 + u) * 32 + lane;
                 const float key = IS_L2 ? a0 + a1 : (a0 + a1) + add;
                 w.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
-            }
-            if (PREFETCH) {
-#pragma unroll
-                for (int u = 0; u < kU; u++)
-#pragma unroll
-                    for (int h = 0; h < M / 16; h++)
-                        cur[u][h] = nxt[u][h];
             }
         }
     }
@@ -315,7 +297,7 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2, typename IdT, int kWarps, bool PREFETCH, int LU>
+template <int M, bool IS_L2, typename IdT, int kWarps, int LU>
 static void launchScanV(
         dim3 grid,
         size_t smem,
@@ -336,7 +318,7 @@ static void launchScanV(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT, kWarps, PREFETCH, LU>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT, kWarps, LU>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
@@ -346,35 +328,11 @@ static void launchScanV(
     CUDA_CHECK_LAST();
 }
 
-// tuning variant (FB200_PQ_VARIANT): warps per CTA / register prefetch / LUT-build unroll
-//   0 = 16 warps, unroll 8 (default)   1 = 16 warps, unroll 1   2 = 16 warps, unroll 2
-//   3 = 8 warps, unroll 1              4 = 8 warps + register prefetch, unroll 1
-static int pqVariant() {
-    const char* e = getenv("FB200_PQ_VARIANT");
-    return e ? atoi(e) : 0;
-}
-static int pqVariantWarps(int v) {
-    return v >= 3 ? 8 : 16;
-}
+constexpr int kScanWarps = 16; // warps per CTA (8 -> 16: 66 -> 60 ms on the N=100M workload)
 
 template <int M, bool IS_L2, typename IdT, typename... Args>
-static void launchScan(int variant, Args... args) {
-    switch (variant) {
-        case 1:
-            launchScanV<M, IS_L2, IdT, 16, false, 1>(args...);
-            break;
-        case 2:
-            launchScanV<M, IS_L2, IdT, 16, false, 2>(args...);
-            break;
-        case 3:
-            launchScanV<M, IS_L2, IdT, 8, false, 1>(args...);
-            break;
-        case 4:
-            launchScanV<M, IS_L2, IdT, 8, true, 1>(args...);
-            break;
-        default:
-            launchScanV<M, IS_L2, IdT, 16, false, 8>(args...);
-    }
+static void launchScan(Args... args) {
+    launchScanV<M, IS_L2, IdT, kScanWarps, 8>(args...);
 }
 
 void runIvfPqScanInterleaved(
@@ -405,8 +363,7 @@ void runIvfPqScanInterleaved(
     const int LIST = std::max(64, next_pow2(k));
     const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
     const size_t listBytes = wide ? SmemTopK<long long>::bytes(LIST, kBuf) : SmemTopK<int>::bytes(LIST, kBuf);
-    const int variant = pqVariant();
-    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * pqVariantWarps(variant);
+    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * kScanWarps;
     FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
     const bool l2 = metric == METRIC_L2;
     int probesPerCta = 1;
@@ -419,7 +376,7 @@ void runIvfPqScanInterleaved(
         dim3 grid((unsigned)chunks, (unsigned)nb);
 #define SCAN(M_, L2_, ID_)                                                                                         \
     launchScan<M_, L2_, ID_>(                                                                                      \
-            variant, grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
+            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
             coarseCentroids, pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(),   \
             partI.as<idx_t>())
 #define SCAN_ID(M_, L2_)        \
