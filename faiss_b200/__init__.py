@@ -528,6 +528,48 @@ def flat_search_exact(res, Y, Q, k, metric=METRIC_L2, device=0):
     return D, I
 
 
+def kmeans_accumulate(res, x, assign, k, device=0):
+    """Per-centroid partial sums [k, d] and counts [k] of the CUDA rows `x` under `assign` (int64 [n]) --
+    the device half of compute_centroids (faiss/impl/ClusteringHelpers.cpp:101-172); the caller
+    all-reduces them across shards and divides."""
+    import torch
+
+    assert x.is_cuda and assign.is_cuda
+    res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
+    n, d = x.shape
+    sums = torch.zeros((k, d), dtype=torch.float32, device=x.device)
+    counts = torch.zeros((k,), dtype=torch.float32, device=x.device)
+    check(
+        lib.b200_kmeans_update(
+            res._h, int(device), _ptr(x, _c_f), _ptr(assign, _c_i64), ctypes.c_int64(n), int(d), ctypes.c_int64(k),
+            _ptr(sums, _c_f), _ptr(counts, _c_f), None,
+        )
+    )
+    return sums, counts
+
+
+def rand_perm(n, seed):
+    """faiss::rand_perm (faiss/utils/random.cpp:130-142), host."""
+    perm = np.empty(int(n), dtype=np.int32)
+    check(lib.faiss_b200_rand_perm(perm.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.c_size_t(int(n)), ctypes.c_int64(int(seed))))
+    return perm
+
+
+def split_clusters(hassign, centroids, n):
+    """faiss split_clusters (faiss/impl/ClusteringHelpers.cpp:177-240) in place on host arrays; returns nsplit."""
+    k, d = centroids.shape
+    assert hassign.dtype == np.float32 and centroids.dtype == np.float32
+    ns = ctypes.c_int(0)
+    fp = ctypes.POINTER(ctypes.c_float)
+    check(
+        lib.faiss_b200_split_clusters(
+            ctypes.c_size_t(d), ctypes.c_size_t(k), ctypes.c_size_t(int(n)), hassign.ctypes.data_as(fp), centroids.ctypes.data_as(fp),
+            ctypes.byref(ns),
+        )
+    )
+    return ns.value
+
+
 def topk_merge(res, D_in, I_in, k, metric=METRIC_L2, id_offsets=None, device=0):
     """D_in/I_in: CUDA tensors [nq, nshard, k_in] -> merged [nq, k] (role of merge_knn_results)."""
     import torch

@@ -13,7 +13,7 @@ import ctypes
 
 import numpy as np
 
-from . import _c_f, _c_i64, _ptr, check, lib, topk_merge
+from . import _c_f, _c_i64, _ptr, check, lib, rand_perm, split_clusters, topk_merge
 
 
 def shard_bounds(n, rank, world):
@@ -103,3 +103,59 @@ class ShardedSearcher:
             aI[s][m] += self.offsets[s]
         mD, mI = merge_host(allD.numpy(), aI, k, self.metric)
         return torch.from_numpy(mD), torch.from_numpy(mI)
+
+
+def sharded_kmeans(x_local, k, niter, local_assign, local_accumulate, seed=1234, group=None):
+    """k-means with the training set sharded over the ranks (contiguous, rank order) and the centroid
+    table replicated: faiss::Clustering::train (faiss/Clustering.cpp:60-380) with the per-iteration
+    reduction of SURVEY 8(e) -- all-reduce(sum) of the per-centroid partial sums, counts and the
+    objective.  Everything else follows the single-process algorithm on the concatenated set:
+    initial centroids = rows rand_perm(n_total, seed + 1)[:k], empty clusters refilled by the
+    reference's deterministic split_clusters on every rank identically.
+
+    x_local:          this rank's rows, torch tensor [n_local, d] (CUDA under NCCL, CPU under gloo)
+    local_assign:     (centroids, x_local) -> (sqdist [n_local], assign int64 [n_local])   -- Flat k=1 search
+    local_accumulate: (x_local, assign, k) -> (sums [k, d], counts [k]) float32, same device as x_local
+    Returns (centroids [k, d] tensor on x_local's device, objective per iteration as numpy float32).
+    Subsampling to max_points_per_centroid is the caller's job (each rank passes the rows it wants used)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_local, d = x_local.shape
+    dev = x_local.device
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(n_local), group=group)
+    n_total = int(sum(sizes))
+    off = int(sum(sizes[:rank]))
+    assert n_total >= k, "need at least k training points"
+    # ---- initial centroids: the global rows perm[:k]; every row is owned by exactly one rank
+    perm = rand_perm(n_total, seed + 1)[:k].astype(np.int64)
+    mine = (perm >= off) & (perm < off + n_local)
+    cent = torch.zeros((k, d), dtype=torch.float32, device=dev)
+    if mine.any():
+        rows = torch.from_numpy(perm[mine] - off).to(dev)
+        cent[torch.from_numpy(np.nonzero(mine)[0]).to(dev)] = x_local[rows]
+    dist.all_reduce(cent, op=dist.ReduceOp.SUM, group=group)
+    objs = []
+    for _ in range(niter):
+        dis, assign = local_assign(cent, x_local)
+        sums, counts = local_accumulate(x_local, assign, k)
+        # one packed reduction per iteration: [k, d] sums | k counts | objective
+        packed = torch.cat([sums.reshape(-1), counts.reshape(-1), dis.double().sum().float().reshape(1)])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        sums = packed[: k * d].reshape(k, d)
+        counts = packed[k * d : k * d + k]
+        objs.append(float(packed[-1]))
+        nz = counts > 0
+        new = torch.zeros_like(cent)
+        new[nz] = sums[nz] * (1.0 / counts[nz]).unsqueeze(1)
+        # empty clusters: the reference's split_clusters on the host (k x d floats), identical on every rank
+        if bool((~nz).any()):
+            h = counts.cpu().numpy().astype(np.float32)
+            c = new.cpu().numpy()
+            split_clusters(h, c, n_total)
+            new = torch.from_numpy(c).to(dev)
+        cent = new
+    return cent, np.array(objs, dtype=np.float32)

@@ -56,3 +56,51 @@ def test_sharded_search_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def _kmeans_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from faiss_b200.distributed import shard_bounds, sharded_kmeans
+    from oracle import oracle_np as o
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rs = np.random.RandomState(5)
+    N, d, k, niter = 3001, 8, 37, 6
+    # integer-valued rows: partial sums are exact in fp32 whatever the reduction order, so the sharded
+    # run must reproduce the single-process algorithm; a far-away blob forces empty clusters -> split_clusters
+    x = np.floor(rs.rand(N, d) * 16).astype(np.float32)
+    x[:40] += 500.0
+    i0, i1 = shard_bounds(N, rank, world)
+
+    def local_assign(cent, xl):
+        D, I = o.knn_flat(xl.numpy(), cent.numpy(), 1, 1)
+        return torch.from_numpy(D[:, 0].copy()), torch.from_numpy(I[:, 0].copy())
+
+    def local_accumulate(xl, assign, kk):
+        sums = np.zeros((kk, xl.shape[1]), dtype=np.float64)
+        np.add.at(sums, assign.numpy(), xl.numpy().astype(np.float64))
+        counts = np.bincount(assign.numpy(), minlength=kk).astype(np.float32)
+        return torch.from_numpy(sums.astype(np.float32)), torch.from_numpy(counts)
+
+    cent, objs = sharded_kmeans(torch.from_numpy(x[i0:i1]), k, niter, local_assign, local_accumulate, seed=1234)
+    rc, robj = o.kmeans(x, k, niter=niter, seed=1234, max_points_per_centroid=1 << 20)
+    ok = bool(np.allclose(cent.numpy(), rc, rtol=1e-6, atol=1e-6) and np.allclose(objs, robj, rtol=1e-6))
+    q.put((rank, ok, float(np.abs(cent.numpy() - rc).max())))
+    dist.destroy_process_group()
+
+
+def test_sharded_kmeans_gloo_world2():
+    """training set split over 2 ranks, all-reduce of sums | counts | objective per iteration ==
+    the single-process reference algorithm on the concatenated set (incl. split_clusters)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_kmeans_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
