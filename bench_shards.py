@@ -3,7 +3,7 @@
 one node (IndexShards semantics), coarse quantiser trained by sharded k-means.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      bench_shards.py --gpus N [--n 1000000000 --d 96 --nlist 65536 --m 32 --nprobe 32]
+      bench_shards.py --gpus N [--ntotal 1000000000 --d 96 --nlist 65536 --m 32 --nprobe 32]
 
 One process per GPU.  Per rank: its contiguous slice of the database and of the training set.
   * train: `faiss_b200.distributed.sharded_kmeans` -- Flat k=1 assignment on the tcgen05 path against the
@@ -13,7 +13,7 @@ One process per GPU.  Per rank: its contiguous slice of the database and of the 
   * search: every query to every shard, ONE all-gather of the per-shard [nq, k] (fp32 | int64) + device
     merge (`ShardedSearcher`), ids translated like successive_ids.
 Prints one JSON line (rank 0).  configs[4] itself is N=1e9 on 8 GPUs (125M vectors per GPU); the defaults
-here are sized per GPU the same way (--n defaults to 125M x world).
+here are sized per GPU the same way (--ntotal defaults to 125M x world).
 """
 import argparse
 import ctypes
@@ -35,7 +35,7 @@ def log(*a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--ntotal", type=int, default=None)
     ap.add_argument("--d", type=int, default=96)
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--m", type=int, default=32)
@@ -62,7 +62,7 @@ def main():
     from bench import ClockSampler, peaks
     from faiss_b200.distributed import ShardedSearcher, shard_bounds, sharded_kmeans
 
-    N = args.n or 125_000_000 * world
+    N = args.ntotal or 125_000_000 * world
     d, nlist, M, nq, k = args.d, args.nlist, args.m, args.nq, args.k
     res = fb.StandardGpuResources()
     res.setDefaultStream(local_rank, torch.cuda.current_stream(dev).cuda_stream)

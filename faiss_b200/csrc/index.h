@@ -381,6 +381,9 @@ class GpuIndexIVF : public GpuIndex {
     size_t nprobe = 1;
     size_t max_codes = 0;
     GpuIndexFlat* quantizer = nullptr;
+    // bumped whenever the coarse centroids are (re)installed through this class (train, setCoarseCentroids);
+    // derived classes key centroid-dependent side tables on it
+    uint64_t coarseEpoch = 0;
     bool own_fields = true;
     ClusteringParameters cp;
 
@@ -472,10 +475,16 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
     int getCentroidsPerSubQuantizer() const {
         return 1 << nbits_;
     }
+    // Precomputed term-2 table  T2[list][code][m] = ||y||^2 + 2 <centroid_list|m, y>  (the role of
+    // faiss/gpu/impl/IVFPQ.cu:362-489 and IndexIVFPQ::precompute_table, faiss/IndexIVFPQ.cpp:376-458).
+    // With it the per-(query, list) lookup table is T2[list] + (-2 <x|m, y>) -- one load and one add per
+    // entry instead of dsub multiply-adds, which is what matters when lists are short (nlist = 65536).
+    // L2 + interleaved layout only.  Policy: on when explicitly enabled; otherwise "auto" = the table is at
+    // most precomputed_table_max_bytes (2 GiB, faiss/IndexIVFPQ.cpp:345) AND lists are short (< 4096 vectors
+    // on average) -- with long lists the direct on-chip build is faster (see GpuIndexIVFPQ::precomputedActive_).
     void setPrecomputedCodes(bool enable) {
-        // the fused scan builds the per-(query,list) table on chip; a precomputed term-2 table
-        // (faiss/gpu/impl/IVFPQ.cu:362-489) would only add HBM traffic.  Accepted, ignored.
         usePrecomputed_ = enable;
+        precomputedExplicit_ = true;
     }
     bool getPrecomputedCodes() const {
         return usePrecomputed_;
@@ -492,7 +501,14 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
     void scanImpl_(idx_t, const float*, const idx_t*, const float*, int, int, float*, idx_t*) const override;
 
     int M_, nbits_;
+    bool precomputedActive_() const;
+    void ensureTerm2_() const;
+
     bool usePrecomputed_ = false;
+    bool precomputedExplicit_ = false;
+    uint64_t pqEpoch_ = 0;
+    mutable DeviceVector<float> term2_; // [nlist][256][M]
+    mutable uint64_t term2Key_ = ~uint64_t(0);
     DeviceVector<float> pqCentroids_;  // [M][256][dsub]
     DeviceVector<float> pqCentroidsT_; // [256][M][dsub] (LUT build reads it coalesced)
 };

@@ -122,8 +122,8 @@ __device__ void merge_and_write(
 // live across the probes of the chunk, so the number of candidates that pass the threshold grows with
 // log(vectors scanned per CTA), not with the number of (query, probe) pairs; per probe only the LUT is
 // rebuilt.  Keys: L2 -> sum of LUT entries; IP -> -(q.centroid) - sum (coarse term folded in per probe).
-template <int M, bool IS_L2, typename IdT, int kWarps, int LU>
-__global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int LU>
+__global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
         const idx_t* __restrict__ probes,
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         int probesPerCta,
         const float* __restrict__ coarse,
         const float* __restrict__ pqT, // [256][M][dsub]
+        const float* __restrict__ term2, // PRECOMP: [nlist][256][M]
         const int64_t* __restrict__ listStart,
         const int* __restrict__ listLen,
         const uint8_t* __restrict__ arenaCodes,
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         int LIST,
         float* __restrict__ partD,
         idx_t* __restrict__ partI) {
+    static_assert(!PRECOMP || IS_L2, "precomputed tables are an L2 decomposition");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int q = blockIdx.y, chunk = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -163,6 +165,72 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
     // counter to balance the per-probe barrier, 59.2 vs 57.7 ms; prefetch.global.L2 of the next chunk, 60.1.)
     constexpr int kU = 4;
     constexpr int kStride = kWarps * kU;
+    constexpr int kThreads = kWarps * 32;
+    constexpr int kEntriesPerThread = 256 * M / kThreads;
+    static_assert(256 * M % kThreads == 0, "LUT entries must divide evenly among the threads");
+
+    // direct LUT entry e = c*M + m from the vector r[d] in shared memory:
+    //   L2: ||r|m - y||^2 (r = query - list centroid);  IP / PRECOMP term 3: <r|m, y> (r = query)
+    auto entry = [&](int e, bool l2form) {
+        const int c = e / M, m = e - c * M;
+        const float* cp = pqT + (size_t)e * dsub;
+        const float* rp = rs + m * dsub;
+        float acc = 0.f;
+        if ((dsub & 3) == 0) {
+            for (int j = 0; j < dsub; j += 4) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cp + j));
+                const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+                if (l2form) {
+                    float d0 = rv.x - cv.x, d1 = rv.y - cv.y, d2 = rv.z - cv.z, d3 = rv.w - cv.w;
+                    acc = fmaf(d0, d0, acc);
+                    acc = fmaf(d1, d1, acc);
+                    acc = fmaf(d2, d2, acc);
+                    acc = fmaf(d3, d3, acc);
+                } else {
+                    acc = fmaf(rv.x, cv.x, acc);
+                    acc = fmaf(rv.y, cv.y, acc);
+                    acc = fmaf(rv.z, cv.z, acc);
+                    acc = fmaf(rv.w, cv.w, acc);
+                }
+            }
+        } else {
+            for (int j = 0; j < dsub; j++) {
+                if (l2form) {
+                    float df = rp[j] - cp[j];
+                    acc = fmaf(df, df, acc);
+                } else {
+                    acc = fmaf(rp[j], cp[j], acc);
+                }
+            }
+        }
+        return acc;
+    };
+    auto store = [&](int e, float val) {
+        const int c = e / M, m = e - c * M;
+#pragma unroll
+        for (int s = 0; s < kLutSlots; s += M)
+            lut[c * kLutSlots + s + m] = val; // entry (c, m) -> slots m, m+M, ... (< 64), conflict-free
+    };
+
+    // Query-only part, once per CTA.  IP: the whole LUT (-<x|m, y> does not depend on the list).
+    // PRECOMP: term 3 = -2 <x|m, y> for this thread's entries, kept in registers across the probes.
+    float t3[PRECOMP ? kEntriesPerThread : 1];
+    if (!IS_L2 || PRECOMP) {
+        for (int i = threadIdx.x; i < d; i += blockDim.x)
+            rs[i] = Q[(int64_t)q * d + i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kEntriesPerThread; i++) {
+            const int e = threadIdx.x + i * kThreads;
+            const float dot = entry(e, false);
+            if (PRECOMP)
+                t3[i] = -2.f * dot;
+            else
+                store(e, -dot);
+        }
+        __syncthreads();
+    }
+
     const int pEnd = min(nprobe, (chunk + 1) * probesPerCta);
     for (int p = chunk * probesPerCta; p < pEnd; p++) {
         const idx_t l = probes[(int64_t)q * nprobe + p];
@@ -174,54 +242,42 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
         const int ngroups = (len + 31) >> 5;
         if (ngroups == 0)
             continue;
-        __syncthreads(); // every warp is done with the previous probe's LUT (and its last claim)
-        for (int i = threadIdx.x; i < d; i += blockDim.x) {
-            float v = Q[(int64_t)q * d + i];
-            rs[i] = IS_L2 ? v - coarse[l * d + i] : v;
-        }
-        __syncthreads();
-        // ---- LUT: entry (c, m) -> slots m, m+M, ... (< 64).  e = c*M + m: coalesced pqT reads, conflict-free writes
-#pragma unroll LU
-        for (int e = threadIdx.x; e < 256 * M; e += kWarps * 32) {
-            const int c = e / M, m = e - c * M;
-            const float* cp = pqT + (size_t)e * dsub;
-            const float* rp = rs + m * dsub;
-            float acc = 0.f;
-            if ((dsub & 3) == 0) {
-                for (int j = 0; j < dsub; j += 4) {
-                    const float4 cv = __ldg(reinterpret_cast<const float4*>(cp + j));
-                    const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-                    if (IS_L2) {
-                        float d0 = rv.x - cv.x, d1 = rv.y - cv.y, d2 = rv.z - cv.z, d3 = rv.w - cv.w;
-                        acc = fmaf(d0, d0, acc);
-                        acc = fmaf(d1, d1, acc);
-                        acc = fmaf(d2, d2, acc);
-                        acc = fmaf(d3, d3, acc);
-                    } else {
-                        acc = fmaf(rv.x, cv.x, acc);
-                        acc = fmaf(rv.y, cv.y, acc);
-                        acc = fmaf(rv.z, cv.z, acc);
-                        acc = fmaf(rv.w, cv.w, acc);
-                    }
-                }
-            } else {
-                for (int j = 0; j < dsub; j++) {
-                    if (IS_L2) {
-                        float df = rp[j] - cp[j];
-                        acc = fmaf(df, df, acc);
-                    } else {
-                        acc = fmaf(rp[j], cp[j], acc);
-                    }
-                }
-            }
-            const float val = IS_L2 ? acc : -acc;
+        float term1 = 0.f;
+        if (IS_L2) {
+            __syncthreads(); // every warp is done with the previous probe's LUT
+            if (PRECOMP) {
+                // LUT = T2[list] + term 3 (one coalesced load and one add per entry); term 1 = ||x - c||^2 is
+                // recomputed here by every warp identically, so the result does not depend on the caller's
+                // coarse distances (search == search_preassigned bit for bit)
+                const float* t2 = term2 + (size_t)l * 256 * M;
+                float v2[kEntriesPerThread];
 #pragma unroll
-            for (int s = 0; s < kLutSlots; s += M)
-                lut[c * kLutSlots + s + m] = val;
+                for (int i = 0; i < kEntriesPerThread; i++)
+                    v2[i] = __ldg(t2 + threadIdx.x + i * kThreads);
+                float part = 0.f;
+                for (int i = lane; i < d; i += 32) {
+                    const float df = rs[i] - __ldg(coarse + l * d + i);
+                    part = fmaf(df, df, part);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    part += __shfl_xor_sync(kFullMask, part, o);
+                term1 = part;
+#pragma unroll
+                for (int i = 0; i < kEntriesPerThread; i++)
+                    store(threadIdx.x + i * kThreads, v2[i] + t3[i]);
+            } else {
+                for (int i = threadIdx.x; i < d; i += blockDim.x)
+                    rs[i] = Q[(int64_t)q * d + i] - coarse[l * d + i];
+                __syncthreads();
+#pragma unroll LU
+                for (int e = threadIdx.x; e < 256 * M; e += kThreads)
+                    store(e, entry(e, true));
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
-        const float add = IS_L2 ? 0.f : -coarseDis[(int64_t)q * nprobe + p];
+        const float add = IS_L2 ? term1 : -coarseDis[(int64_t)q * nprobe + p];
         for (int g0 = warp * kU; g0 < ngroups; g0 += kStride) {
             uint4 cur[kU][M / 16];
 #pragma unroll
@@ -254,7 +310,7 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
                     }
                 }
                 const int v = (g0 + u) * 32 + lane;
-                const float key = IS_L2 ? a0 + a1 : (a0 + a1) + add;
+                const float key = (IS_L2 && !PRECOMP) ? a0 + a1 : (a0 + a1) + add;
                 w.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
             }
         }
@@ -262,7 +318,41 @@ __global__ void __launch_bounds__(kWarps * 32) ivfpq_scan_interleaved_kernel(
     merge_and_write<IdT, kWarps>(w, warp, lists, perWarp, LIST, k, arenaIds, oD, oI);
 }
 
+// T2[l][e] (e = c*M + m) = ||y_e||^2 + 2 <centroid_l | m, y_e>
+__global__ void ivfpq_term2_kernel(
+        const float* __restrict__ coarse, const float* __restrict__ pqT, int64_t nlist, int d, int M, float* __restrict__ term2) {
+    const int64_t l = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 256 * M)
+        return;
+    const int dsub = d / M;
+    const int m = e % M;
+    const float* y = pqT + (size_t)e * dsub;
+    const float* c = coarse + l * d + m * dsub;
+    float acc = 0.f;
+    for (int j = 0; j < dsub; j++) {
+        const float yj = y[j];
+        acc = fmaf(yj, yj, acc);
+        acc = fmaf(2.f * c[j], yj, acc);
+    }
+    term2[(size_t)l * 256 * M + e] = acc;
+}
+
 } // namespace
+
+void runIvfPqPrecomputeTerm2(
+        const float* coarse, const float* pqT, int64_t nlist, int d, int M, float* term2, cudaStream_t stream) {
+    if (nlist == 0)
+        return;
+    FB_THROW_IF_NOT_MSG(nlist <= 65535 * 32, "nlist too large for the term-2 precompute grid");
+    // grid.y is limited to 65535: fold the lists into (x = entries, y = lists) with y chunks
+    for (int64_t l0 = 0; l0 < nlist; l0 += 65535) {
+        const int64_t nl = std::min<int64_t>(65535, nlist - l0);
+        dim3 grid((unsigned)ceil_div(256 * M, 256), (unsigned)nl);
+        ivfpq_term2_kernel<<<grid, 256, 0, stream>>>(coarse + l0 * d, pqT, nl, d, M, term2 + (size_t)l0 * 256 * M);
+        CUDA_CHECK_LAST();
+    }
+}
 
 void runIvfPqScatterInterleaved(
         const uint8_t* codesFlat,
@@ -297,7 +387,7 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2, typename IdT, int kWarps, int LU>
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int LU>
 static void launchScanV(
         dim3 grid,
         size_t smem,
@@ -310,6 +400,7 @@ static void launchScanV(
         int probesPerCta,
         const float* coarse,
         const float* pqT,
+        const float* term2,
         const int64_t* listStart,
         const int* listLen,
         const uint8_t* codes,
@@ -318,21 +409,21 @@ static void launchScanV(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, IdT, kWarps, LU>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, PRECOMP, IdT, kWarps, LU>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
-            Q, d, probes, coarseDis, nprobe, probesPerCta, coarse, pqT, listStart, listLen, codes, ids, k, LIST, partD,
-            partI);
+            Q, d, probes, coarseDis, nprobe, probesPerCta, coarse, pqT, term2, listStart, listLen, codes, ids, k, LIST,
+            partD, partI);
     KernelTiming::end("ivfpq_scan", stream);
     CUDA_CHECK_LAST();
 }
 
 constexpr int kScanWarps = 16; // warps per CTA (8 -> 16: 66 -> 60 ms on the N=100M workload)
 
-template <int M, bool IS_L2, typename IdT, typename... Args>
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, typename... Args>
 static void launchScan(Args... args) {
-    launchScanV<M, IS_L2, IdT, kScanWarps, 8>(args...);
+    launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, 8>(args...);
 }
 
 void runIvfPqScanInterleaved(
@@ -346,6 +437,7 @@ void runIvfPqScanInterleaved(
         int nprobe,
         const float* coarseCentroids,
         const float* pqCentroidsT,
+        const float* term2,
         int M,
         const int64_t* listStart,
         const int* listLen,
@@ -374,28 +466,33 @@ void runIvfPqScanInterleaved(
         auto partD = res->temp(device, sizeof(float) * nb * chunks * k);
         auto partI = res->temp(device, sizeof(idx_t) * nb * chunks * k);
         dim3 grid((unsigned)chunks, (unsigned)nb);
-#define SCAN(M_, L2_, ID_)                                                                                         \
-    launchScan<M_, L2_, ID_>(                                                                                      \
+#define SCAN(M_, L2_, PRE_, ID_)                                                                                   \
+    launchScan<M_, L2_, PRE_, ID_>(                                                                                \
             grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
-            coarseCentroids, pqCentroidsT, listStart, listLen, arenaCodes, arenaIds, k, LIST, partD.as<float>(),   \
-            partI.as<idx_t>())
-#define SCAN_ID(M_, L2_)        \
-    do {                        \
-        if (wide)               \
-            SCAN(M_, L2_, long long); \
-        else                    \
-            SCAN(M_, L2_, int); \
+            coarseCentroids, pqCentroidsT, term2, listStart, listLen, arenaCodes, arenaIds, k, LIST,               \
+            partD.as<float>(), partI.as<idx_t>())
+#define SCAN_ID(M_, L2_, PRE_)          \
+    do {                                \
+        if (wide)                       \
+            SCAN(M_, L2_, PRE_, long long); \
+        else                            \
+            SCAN(M_, L2_, PRE_, int);   \
     } while (0)
+        const bool pre = l2 && term2 != nullptr;
         if (M == 32) {
-            if (l2)
-                SCAN_ID(32, true);
+            if (pre)
+                SCAN_ID(32, true, true);
+            else if (l2)
+                SCAN_ID(32, true, false);
             else
-                SCAN_ID(32, false);
+                SCAN_ID(32, false, false);
         } else {
-            if (l2)
-                SCAN_ID(16, true);
+            if (pre)
+                SCAN_ID(16, true, true);
+            else if (l2)
+                SCAN_ID(16, true, false);
             else
-                SCAN_ID(16, false);
+                SCAN_ID(16, false, false);
         }
 #undef SCAN_ID
 #undef SCAN

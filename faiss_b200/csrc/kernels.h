@@ -278,6 +278,10 @@ void runIvfPqScatterInterleaved(
 void runIvfPqListToInterleaved(const uint8_t* flat, int64_t len, int M, uint8_t* listCodes, cudaStream_t stream);
 void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, uint8_t* flat, cudaStream_t stream);
 
+// T2[l][c][m] = ||y_{m,c}||^2 + 2 <centroid_l restricted to sub-space m, y_{m,c}>   (pqT = [256][M][dsub])
+void runIvfPqPrecomputeTerm2(
+        const float* coarse, const float* pqT, int64_t nlist, int d, int M, float* term2, cudaStream_t stream);
+
 // scan over the interleaved layout; pqCentroidsT is the [ksub][M][dsub] transpose of pqCentroids
 void runIvfPqScanInterleaved(
         GpuResources* res,
@@ -290,6 +294,7 @@ void runIvfPqScanInterleaved(
         int nprobe,
         const float* coarseCentroids,
         const float* pqCentroidsT,
+        const float* term2, // precomputed [nlist][256][M] table (L2) or null
         int M,
         const int64_t* listStart,
         const int* listLen,

@@ -138,6 +138,12 @@ def test_ivfpq_train_add_search_vs_oracle(res, M):
     assert all(np.array_equal(a, b) for a, b in zip(before, after))
     D3, I3 = idx.search(xq, k)
     assert np.array_equal(I, I3)
+    # precomputed term-2 tables (GpuIndexIVFPQConfig::usePrecomputedTables, IndexIVFPQ::precompute_table)
+    # and the direct per-list LUT are two evaluations of the same distance: both must meet the oracle bar
+    for enable in (False, True):
+        idx.setPrecomputedCodes(enable)
+        Dp, Ip = idx.search(xq, k)
+        o.compare_lists(rD, rI, Dp, Ip, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
 
 
 @pytest.mark.parametrize("kind", ["flat40", "flat128", "pq16", "pq32"])
