@@ -256,6 +256,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     import faiss_b200 as fb
     from faiss_b200.distributed import ShardedSearcher, shard_bounds
