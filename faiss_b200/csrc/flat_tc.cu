@@ -655,7 +655,14 @@ void runFlatTcSearch(
 
     CUtensorMap mapY = makeTileMap(Y16, n, dpad, kTileN);
 
-    const int64_t kQBatch = 16384; // queries per pass (bounds the candidate arena)
+    // first round: ~40 k rows (16 tiles at k = 100).  Every score of round 0 becomes a candidate, so a
+    // fixed 16 tiles would make small-k searches (k-means assignment: k = 1, millions of queries) pay 4096
+    // candidates per query for nothing.
+    static const int r0Env = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 0;
+    const int r0Tiles = std::max(r0Env > 0 ? r0Env : std::max(1, (40 * k + kTileN - 1) / kTileN), (k + 127) / 128 * 2);
+    // queries per pass: bounds the candidate arena, whose largest user is the all-pass round 0
+    // (512 KB per query pair and tile) -- 16384 queries at k = 100, up to 131072 for small k
+    const int64_t kQBatch = std::min<int64_t>(131072, std::max<int64_t>(16384, (int64_t)kPairM * 1024 / r0Tiles));
     for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
         const int64_t nq = std::min(kQBatch, nqAll - qb);
         const float* Qb = Q + qb * d;
@@ -696,12 +703,11 @@ void runFlatTcSearch(
             int64_t seen = 0;
             while (seen < T) {
                 // schedule knobs (tuning only): first-round tiles, early / late growth factors
-                static const int r0Tiles = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 16;
                 static const double gEarly = getenv("FB200_TC_G_EARLY") ? atof(getenv("FB200_TC_G_EARLY")) : 4.0;
                 static const double gLate = getenv("FB200_TC_G_LATE") ? atof(getenv("FB200_TC_G_LATE")) : 4.0;
                 static const int64_t lateFrom = getenv("FB200_TC_LATE_FROM") ? atol(getenv("FB200_TC_LATE_FROM")) : 8192;
                 const double g = seen >= lateFrom ? gLate : gEarly;
-                int64_t end = seen == 0 ? std::min<int64_t>(T, std::max(r0Tiles, (k + 127) / 128 * 2))
+                int64_t end = seen == 0 ? std::min<int64_t>(T, r0Tiles)
                                         : std::min<int64_t>(T, (int64_t)(seen * g));
                 if (T - end < end / 4)
                     end = T; // do not leave a sliver for an extra round
