@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ntrain", type=int, default=1 << 20)
+    ap.add_argument("--recall-queries", type=int, default=100, help="queries checked against exact fp32 ground truth (0 = skip)")
     args = ap.parse_args()
     N = args.n or (100_000_000 if args.index == "ivfpq" else 10_000_000)
     nprobe = args.nprobe or (32 if args.index == "ivfpq" else 64)
@@ -128,6 +129,27 @@ def main():
         index.search(xq_pin.numpy(), k, D=D_pin.numpy(), I=I_pin.numpy())
     e2e_ms = (time.time() - t0) * 1e3 / args.steps
 
+    # recall vs exact ground truth on a query subset: the database is regenerated chunk by chunk (same
+    # seeds as the add loop), each chunk searched exactly (fp32 SIMT kernel), chunk results merged
+    recall = None
+    if args.recall_queries > 0:
+        nr = min(args.recall_queries, nq)
+        bestD = torch.full((nr, k), float("inf"), device=dev)
+        bestI = torch.full((nr, k), -1, dtype=torch.int64, device=dev)
+        for c0 in range(0, N, CH):
+            xb = gen(min(CH, N - c0), 1234 + c0 // CH)
+            cD, cI = fb.flat_search_exact(res, xb, xq[:nr].contiguous(), k)
+            allD = torch.cat([bestD, cD], dim=1)
+            allI = torch.cat([bestI, cI + c0], dim=1)
+            o_ = torch.argsort(allD, dim=1, stable=True)[:, :k]
+            bestD, bestI = torch.gather(allD, 1, o_), torch.gather(allI, 1, o_)
+            del xb
+        D, I = index.search(xq[:nr].contiguous(), k)
+        inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(I.cpu().numpy(), bestI.cpu().numpy()))
+        r1 = float((I[:, :k] == bestI[:, :1]).any(dim=1).float().mean())
+        recall = {"queries": nr, "intersection_recall_at_k": inter / float(nr * k), "recall_1_at_k": r1,
+                  "note": "vs exact fp32 ground truth; uniform random d=%d data is a worst case for IVF/PQ recall (SURVEY 8d)" % d}
+
     pk, src = peaks()
     roof = {"bound": "hbm", "unit": "GB/s", "peak": float(pk["hbm_gbs"]), "peak_source": src + " copy bandwidth (MEASURED_PEAKS.json)",
             "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "vectors_scanned_per_step": scanned}
@@ -142,7 +164,7 @@ def main():
                "list_len_mean": float(lens.mean()), "list_len_max": int(lens.max()), "train_s": t_train, "add_s": t_add, "add_vec_per_s": N / t_add},
            "clocks": clocks, "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
                                      "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12},
-           "gpu_launches": int(launches), "roofline": roof}
+           "gpu_launches": int(launches), "roofline": roof, "recall": recall}
     print(json.dumps(out), flush=True)
 
 
