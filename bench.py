@@ -256,10 +256,18 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        # keep stdout to the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=device)
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout when the first
+        # communicator is created (any NCCL_DEBUG level >= VERSION), so that happens with fd 1 -> fd 2
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.all_reduce(torch.zeros(1, device=device))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     import faiss_b200 as fb
     from faiss_b200.distributed import ShardedSearcher, shard_bounds
 

@@ -56,9 +56,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
-    dist.init_process_group("nccl", device_id=dev)
+    # NCCL prints its version banner to stdout when the first communicator is created: keep stdout to
+    # the one JSON line by creating it with fd 1 -> fd 2
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
 
     import faiss_b200 as fb
     from bench import ClockSampler, peaks
