@@ -170,10 +170,34 @@ def ivfpq_lut(q, c_list, pq_centroids, metric=METRIC_L2):
     return (qq * pq_centroids).sum(-1, dtype=np.float32)
 
 
-def ivfpq_search(xq, k, nprobe, centroids, pq_centroids, lists_codes, lists_ids, metric=METRIC_L2, probes=None):
+def ivfpq_precomputed_table(centroids, pq_centroids):
+    """IndexIVFPQ::precompute_table (faiss/IndexIVFPQ.cpp:376-458), use_precomputed_table = 1:
+    T2[list][m][c] = ||y_{m,c}||^2 + 2 <centroid_list | m, y_{m,c}>."""
+    M, ksub, dsub = pq_centroids.shape
+    nlist = centroids.shape[0]
+    r_norms = (pq_centroids.astype(np.float32) ** 2).sum(-1, dtype=np.float32)  # [M, ksub]
+    c = centroids.astype(np.float32).reshape(nlist, M, 1, dsub)
+    cross = (c * pq_centroids[None]).sum(-1, dtype=np.float32)  # [nlist, M, ksub]
+    return r_norms[None] + np.float32(2.0) * cross
+
+
+def ivfpq_lut_precomputed(q, c_list, t2_list, pq_centroids):
+    """Precomputed-table form of the L2 table (IVFPQ_QueryTables.cpp:126-192): the distance is
+    term1 + sum_m (T2[list][m][c] - 2 <q|m, y_{m,c}>) with term1 = ||q - c_list||^2.  Returns (term1, tab)."""
+    M, ksub, dsub = pq_centroids.shape
+    qq = q.astype(np.float32).reshape(M, 1, dsub)
+    t3 = np.float32(-2.0) * (qq * pq_centroids).sum(-1, dtype=np.float32)
+    r = (q - c_list).astype(np.float32)
+    return np.float32((r * r).sum(dtype=np.float32)), (t2_list + t3).astype(np.float32)
+
+
+def ivfpq_search(xq, k, nprobe, centroids, pq_centroids, lists_codes, lists_ids, metric=METRIC_L2, probes=None, precomputed=False):
     """IndexIVFPQ::search = coarse quantisation + search_preassigned with the table scanner
-    (faiss/IndexIVF.cpp:305-760, faiss/impl/pq_code_distance/IVFPQScanner_impl.h:122-198)."""
+    (faiss/IndexIVF.cpp:305-760, faiss/impl/pq_code_distance/IVFPQScanner_impl.h:122-198).
+    precomputed=True evaluates the L2 distance in the precomputed-table decomposition instead of
+    the residual form (the CPU reference picks either, `use_precomputed_table`)."""
     M = pq_centroids.shape[0]
+    t2 = ivfpq_precomputed_table(centroids, pq_centroids) if (precomputed and metric == METRIC_L2) else None
     nq = xq.shape[0]
     if probes is None:
         cD, probes = knn_flat(xq, centroids, nprobe, metric)
@@ -191,8 +215,12 @@ def ivfpq_search(xq, k, nprobe, centroids, pq_centroids, lists_codes, lists_ids,
             codes = lists_codes[l].reshape(-1, M)
             if codes.shape[0] == 0:
                 continue
-            tab = ivfpq_lut(xq[qi], centroids[l], pq_centroids, metric)
-            dis = tab[mrange[None, :], codes].sum(1, dtype=np.float32)
+            if t2 is not None:
+                term1, tab = ivfpq_lut_precomputed(xq[qi], centroids[l], t2[l], pq_centroids)
+                dis = tab[mrange[None, :], codes].sum(1, dtype=np.float32) + term1
+            else:
+                tab = ivfpq_lut(xq[qi], centroids[l], pq_centroids, metric)
+                dis = tab[mrange[None, :], codes].sum(1, dtype=np.float32)
             if metric == METRIC_INNER_PRODUCT:
                 dis = dis + np.float32(np.dot(xq[qi].astype(np.float32), centroids[l].astype(np.float32)))
                 dis = -dis

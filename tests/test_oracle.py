@@ -132,3 +132,29 @@ def test_precomputed_table_on_off_same_ids(ref):
     D0, I0 = ivf.search(xq, 10)
     assert (I0 == I1).mean() > 0.98
     assert np.allclose(D0, D1, rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_precomputed_form_vs_reference(ref):
+    """the numpy restatement of the precomputed-table decomposition (what the GPU scan evaluates when
+    usePrecomputedTables is active) against the reference CPU index with use_precomputed_table = 1, and
+    against the residual form: same ids up to near-ties, distances within 1e-4 relative"""
+    rs = np.random.RandomState(7)
+    d, nlist, M, k, nprobe = 32, 16, 8, 10, 4
+    xb = rs.rand(6000, d).astype(np.float32)
+    xq = rs.rand(30, d).astype(np.float32)
+    ivf = ref.IndexIVFPQ(d, nlist, M, 8, 1)
+    ivf.set_cp(niter=4)
+    ivf.set_pq_cp(niter=4)
+    ivf.train(xb)
+    ivf.add(xb)
+    ivf.set_nprobe(nprobe)
+    ivf.set_precomputed_table(1)
+    rD, rI = ivf.search(xq, k)
+    cent = ivf.centroids()
+    pq = ivf.pq_centroids()
+    lists = [ivf.get_list(l) for l in range(nlist)]
+    lc, li = [c for c, _ in lists], [i for _, i in lists]
+    D1, I1 = o.ivfpq_search(xq, k, nprobe, cent, pq, lc, li, 1, precomputed=True)
+    D0, I0 = o.ivfpq_search(xq, k, nprobe, cent, pq, lc, li, 1, precomputed=False)
+    o.compare_lists(rD, rI, D1, I1, eps=1e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+    o.compare_lists(D0, I0, D1, I1, eps=1e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
