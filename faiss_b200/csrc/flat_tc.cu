@@ -9,15 +9,17 @@
 //     fp16 after a power-of-two scaling; the dot product runs on tcgen05.mma (kind::f16, fp32
 //     accumulate in TMEM).  |approx - exact| <= eps_q, a rigorous bound from the fp16 rounding
 //     model (10 mantissa bits) and the fp32 accumulation.
-//   * Fused filter.  A persistent warp-specialised kernel: warp 0 = TMA producer (query tile once
-//     per work unit, database tiles through a multi-stage mbarrier ring), warp 1 = single-thread
-//     MMA issuer (128x128xK tiles, 4 TMEM accumulator stages), warps 2..9 = epilogue: each thread
-//     owns ONE query row (a TMEM lane) and 64 of the tile's 128 columns; it pulls 32 columns at a
-//     time with tcgen05.ld, adds the per-column bias, and compares the chunk maximum against the
-//     query's threshold held in a register.  Scores never reach HBM; only the rare survivors are
-//     appended (plain stores, no atomics) to a thread-private candidate segment.
-//   * Thresholds come from geometric rounds over a pseudo-randomly permuted tile order: round r
-//     scans 3x the rows seen so far; after each round a small kernel folds the new candidates into
+//   * Fused filter (flat_tc_kernel.cuh).  A persistent warp-specialised kernel: warp 0 = TMA producer
+//     (two query tiles once per work unit, 256-row database tiles through an mbarrier ring), warp 1 =
+//     single-thread MMA issuer (128x256xK tiles, two TMEM accumulators = the unit's two query tiles),
+//     16 epilogue warps: each thread owns ONE query row (a TMEM lane) and 64 of a tile's 256 columns,
+//     pulls 32 columns at a time with tcgen05.ld, folds the RAW accumulators with an FMNMX3 tree and
+//     compares one bound per chunk against the query's threshold held in a register -- the fp16 copy
+//     is stored sorted by norm, so the tile's maximum bias bounds every row's bias tightly.  Scores
+//     never reach HBM; only the rare survivors are appended (plain stores, no atomics) to a
+//     thread-private candidate segment.
+//   * Thresholds come from geometric rounds over a pseudo-randomly permuted tile order: round 0
+//     scans ~40 k rows, round r 3x the rows seen so far; after each round a small kernel folds the new candidates into
 //     a per-query sorted base list and sets threshold = (k-th best approx score) - 2*eps_q, which
 //     provably keeps every true top-k member.
 //   * Certified exact result.  The final kernel re-ranks the base list with the library's canonical
