@@ -91,3 +91,38 @@ def test_shard_bounds_contiguous():
     b = [shard_bounds(n, r, w) for r in range(w)]
     assert b[0][0] == 0 and b[-1][1] == n
     assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_cloner_shard_ivf_lists_rules():
+    """shard_type 1 / 2 / 4 of ToGpuClonerMultiple::copy_ivf_shard (faiss/gpu/GpuCloner.cpp:287-322) on the
+    ArrayInvertedLists payload: a partition, list order kept, the reference's boundaries"""
+    from faiss_b200 import cloner
+
+    rs = np.random.RandomState(2)
+    nlist, code_size, ntotal = 13, 6, 1000
+    assign = rs.randint(0, nlist, ntotal)
+    all_ids = rs.permutation(ntotal).astype(np.int64)
+    ids = [all_ids[assign == l] for l in range(nlist)]
+    codes = [rs.randint(0, 256, (a.size, code_size)).astype(np.uint8).reshape(-1) for a in ids]
+    for st in (cloner.SHARD_BY_ID_MOD, cloner.SHARD_BY_ID_RANGE, cloner.SHARD_BY_LIST_RANGE):
+        for n in (1, 2, 3, 8):
+            parts = cloner.shard_ivf_lists(codes, ids, code_size, n, st)
+            assert len(parts) == n
+            for l in range(nlist):
+                got_ids = np.concatenate([p[1][l] for p in parts])
+                assert sorted(got_ids.tolist()) == sorted(ids[l].tolist())  # partition of the list
+                for i, (ci, ii) in enumerate(parts):
+                    # order inside the list is the original order, codes travel with their ids
+                    pos = {int(v): j for j, v in enumerate(ids[l])}
+                    js = [pos[int(v)] for v in ii[l]]
+                    assert js == sorted(js)
+                    ref_codes = codes[l].reshape(-1, code_size)[js].reshape(-1)
+                    assert np.array_equal(ci[l], ref_codes)
+                    if st == cloner.SHARD_BY_ID_MOD:
+                        assert ((ii[l] % n) == i).all()
+                    elif st == cloner.SHARD_BY_ID_RANGE:
+                        assert ((ii[l] >= i * ntotal // n) & (ii[l] < (i + 1) * ntotal // n)).all()
+                    else:
+                        assert ii[l].size == (ids[l].size if i * nlist // n <= l < (i + 1) * nlist // n else 0)
+    with pytest.raises(ValueError):
+        cloner.shard_ivf_lists(codes, ids, code_size, 2, 3)

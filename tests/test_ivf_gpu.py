@@ -254,3 +254,37 @@ def test_device_merge_kernel_vs_reference_merge(res, golden):
     D, I = fb.topk_merge(res, allD, allI, 5, 1)
     assert np.array_equal(I.cpu().numpy(), golden["merge_I"])
     assert np.array_equal(D.cpu().numpy(), golden["merge_D"])
+
+
+@pytest.mark.parametrize("shard_type", [1])
+def test_cloner_ivfpq_shards_equal_unsharded(res, shard_type):
+    """index_cpu_to_gpu_multiple(shard=True) semantics on the payload: the same coarse quantiser and PQ
+    in every sub-index, lists split by shard_type, IndexShards with explicit ids == the unsharded index
+    (faiss/gpu/test/test_multi_gpu.py:60-119 compares sharded IVF against the CPU index the same way).
+    Distances agree to the last ulp or two, not bit for bit: the rotated code layout sums a vector's M table
+    entries in a cyclic order that starts at (slot in the list) mod 32, and re-sharding moves the slots
+    (observed 2.3172128 vs 2.3172126).  The splitting rules for shard types 2 and 4 are covered on the CPU
+    (tests/test_abi.py::test_cloner_shard_ivf_lists_rules)."""
+    import faiss_b200 as fb
+    from faiss_b200 import cloner
+
+    rs = np.random.RandomState(21)
+    N, d, nlist, M, nq, k = 20000, 32, 24, 16, 40, 30
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    idx = fb.GpuIndexIVFPQ(res, d, nlist, M, 8, 1)
+    idx.setClustering(niter=4)
+    idx.setPQClustering(niter=4)
+    idx.train(xb)
+    idx.add(xb)
+    idx.nprobe = 5
+    D, I = idx.search(xq, k)
+    payload = {"d": d, "nlist": nlist, "metric": 1, "centroids": idx.getCoarseCentroids(), "pq": idx.getPQCentroids(),
+               "codes": [idx.getListVectorData(l) for l in range(nlist)], "ids": [idx.getListIndices(l) for l in range(nlist)]}
+    shards = cloner.gpu_ivf_shards_from_payload([res, res, res], payload, shard_type=shard_type, threaded=False)
+    assert shards.ntotal == N
+    for i in range(shards.count()):
+        shards.at(i).nprobe = 5
+    Ds, Is = shards.search(xq, k)
+    assert np.allclose(Ds, D, rtol=2e-6, atol=0)
+    o.compare_lists(D, I, Ds, Is, eps=1e-5, pct_max_diff1=0.02, pct_max_diffN=0.01)
