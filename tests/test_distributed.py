@@ -41,6 +41,28 @@ def _worker(rank, world, port, q):
     D, I = s.search(torch.from_numpy(xq), k)
     rD, rI = o.knn_flat(xq, xb, k, 1)
     ok = bool(np.array_equal(I.numpy(), rI) and np.array_equal(D.numpy(), rD) and s.ntotal == N)
+
+    # inner product (descending order, ties by id) through the same exchange
+    def local_search_ip(x, kk):
+        return o.knn_flat(x.numpy(), xb[i0:i1], kk, 0)
+
+    sip = ShardedSearcher(local_search_ip, i1 - i0, 0)
+    D, I = sip.search(torch.from_numpy(xq), k)
+    rD, rI = o.knn_flat(xq, xb, k, 0)
+    ok = ok and bool(np.array_equal(I.numpy(), rI) and np.array_equal(D.numpy(), rD))
+
+    # a database smaller than k: shards pad with id -1 (Heap.cpp:200,224 skips them), the merged tail
+    # is -1 / +inf-like exactly where the unsharded index has no result
+    small = xb[:9]
+    j0, j1 = shard_bounds(9, rank, world)
+
+    def local_search_small(x, kk):
+        return o.knn_flat(x.numpy(), small[j0:j1], kk, 1)
+
+    ss = ShardedSearcher(local_search_small, j1 - j0, 1)
+    D, I = ss.search(torch.from_numpy(xq), 12)
+    rD, rI = o.knn_flat(xq, small, 12, 1)
+    ok = ok and bool(np.array_equal(I.numpy(), rI) and np.array_equal(D.numpy()[:, :9], rD[:, :9]) and (I.numpy()[:, 9:] == -1).all())
     q.put((rank, ok))
     dist.destroy_process_group()
 
