@@ -126,3 +126,40 @@ def test_cloner_shard_ivf_lists_rules():
                         assert ii[l].size == (ids[l].size if i * nlist // n <= l < (i + 1) * nlist // n else 0)
     with pytest.raises(ValueError):
         cloner.shard_ivf_lists(codes, ids, code_size, 2, 3)
+
+
+def test_host_merge_property_vs_reference_live(ref):
+    """merge_knn_results (faiss/utils/Heap.cpp:166-238) vs the library's host merge on random shard
+    results with heavy distance ties, -1 padding (shards with fewer than k results) and both metrics.
+    Distances must be identical; ids identical wherever the distance is not tied (the reference's heap
+    merge leaves the order inside a run of equal distances unspecified; ours is (distance, id))."""
+    from faiss_b200.distributed import merge_host
+
+    rs = np.random.RandomState(123)
+    for trial in range(60):
+        ns, n, k = rs.randint(1, 6), rs.randint(1, 9), rs.randint(1, 17)
+        metric = int(rs.randint(0, 2))
+        allD = np.empty((ns, n, k), dtype=np.float32)
+        allI = np.empty((ns, n, k), dtype=np.int64)
+        for s in range(ns):
+            for q in range(n):
+                m = rs.randint(0, k + 1)  # valid results of this shard for this query
+                d = np.sort(rs.randint(0, 6, m).astype(np.float32))  # few distinct values: many ties
+                if metric == 0:
+                    d = d[::-1]
+                ids = rs.permutation(1000)[:m].astype(np.int64) + 1000 * s  # ids disjoint across shards
+                pad_d = np.float32(np.finfo(np.float32).max) if metric == 1 else np.float32(-np.finfo(np.float32).max)
+                allD[s, q] = np.concatenate([d, np.full(k - m, pad_d, dtype=np.float32)])
+                allI[s, q] = np.concatenate([ids, np.full(k - m, -1, dtype=np.int64)])
+        rD, rI = ref.merge_knn_results(allD, allI, metric)
+        D, I = merge_host(allD, allI, k, metric)
+        valid = rI >= 0
+        assert np.array_equal(valid, I >= 0)
+        assert np.array_equal(D[valid], rD[valid])
+        for q in range(n):
+            for v in np.unique(D[q][valid[q]]):
+                sel = (D[q] == v) & valid[q]
+                # same multiset of ids per tied run unless the run is cut by the k boundary
+                if sel[-1] and valid[q][-1]:
+                    continue
+                assert sorted(I[q][sel].tolist()) == sorted(rI[q][sel].tolist())
