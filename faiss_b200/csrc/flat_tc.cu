@@ -164,8 +164,11 @@ __global__ void tc_prepare_queries_kernel(
         acc += __shfl_xor_sync(kFullMask, acc, o);
     if (lane_id() == 0) {
         float qn = sqrtf(acc) * 1.0001f;
-        // |approx - exact| <= c1*|q||y| + c2*(|y|^2/2 + |q||y|)   (error model)
-        eps[row] = c1 * qn * yMaxNorm + c2 * (0.5f * yMaxNorm * yMaxNorm + qn * yMaxNorm);
+        // |approx score - score implied by the exact kernel's fp32 distance| <= c1*|q||y| + c2*(|q|+|y|)^2
+        // (error model): c1 = fp16 input rounding + TMEM accumulation of q.y, c2 = fp32
+        // rounding of the bias (norms), of the final FMA and of the exact kernel's own sum (d terms)
+        const float qy = qn + yMaxNorm;
+        eps[row] = c1 * qn * yMaxNorm + c2 * qy * qy;
         thr[row] = -CUDART_INF_F;
     }
 }
@@ -653,7 +656,7 @@ void runFlatTcSearch(
 
     // error model constants: fp16 rounding of both operands + fp32 accumulation slack
     const float c1 = 1.01f * (ldexpf(1.f, -10) + (float)dpad * ldexpf(1.f, -22));
-    const float c2 = ldexpf(1.f, -22);
+    const float c2 = (float)(dpad + 16) * ldexpf(1.f, -24);
 
     CUtensorMap mapY = makeTileMap(Y16, n, dpad, kTileN);
 
