@@ -130,6 +130,9 @@ FB200_API int faiss_GpuIndexIVFPQ_new(FaissGpuIndex** p_index, FaissStandardGpuR
 FB200_API int faiss_GpuIndexIVFPQ_setPQCentroids(FaissGpuIndex* index, const float* centroids /* [M][256][dsub] */);
 FB200_API int faiss_GpuIndexIVFPQ_getPQCentroids(const FaissGpuIndex* index, float* centroids_out);
 FB200_API int faiss_GpuIndexIVFPQ_set_pq_clustering(FaissGpuIndex* index, int niter, int seed, int max_points_per_centroid);
+/* GpuIndexIVFPQ::setPrecomputedCodes (faiss/gpu/GpuIndexIVFPQ.h:114-118): force the precomputed term-2 table
+   ([nlist][256][M] floats, L2 only) on or off; untouched, the index follows the CPU reference's "auto" size
+   rule (<= 2 GiB, faiss/IndexIVFPQ.cpp:345) for indexes with short lists.  Results agree to fp32 rounding. */
 FB200_API int faiss_GpuIndexIVFPQ_setPrecomputedCodes(FaissGpuIndex* index, int enable);
 
 /* ---- IndexShards (c_api/IndexShards_c.h:28-40) ---- */
