@@ -314,10 +314,21 @@ def split_clusters(d, k, n, hassign, centroids):
     return nsplit
 
 
-def kmeans(x, k, niter=25, seed=1234, max_points_per_centroid=256):
-    """faiss::Clustering::train_encoded (faiss/Clustering.cpp:60-380) with an exact L2 assignment
-    index: subsample by rand_perm(seed), init = x[rand_perm(seed+1)[:k]], Lloyd iterations with
-    compute_centroids (ClusteringHelpers.cpp:101-172) and split_clusters."""
+def renorm_l2(c):
+    """fvec_renorm_L2 (faiss/utils/distances.cpp:238-251): rows with non-zero norm scaled by 1/sqrtf(||row||^2)."""
+    c = np.asarray(c, dtype=np.float32)
+    nr = (c.astype(np.float32) ** 2).sum(axis=1, dtype=np.float32)
+    inv = np.ones_like(nr)
+    inv[nr > 0] = (np.float32(1.0) / np.sqrt(nr[nr > 0], dtype=np.float32)).astype(np.float32)
+    return (c * inv[:, None]).astype(np.float32)
+
+
+def kmeans(x, k, niter=25, seed=1234, max_points_per_centroid=256, metric=METRIC_L2, spherical=False):
+    """faiss::Clustering::train_encoded (faiss/Clustering.cpp:60-380) with an exact assignment index of
+    the given metric: subsample by rand_perm(seed), init = x[rand_perm(seed+1)[:k]], post_process_centroids
+    (spherical: fvec_renorm_L2, Clustering.cpp:35-45) after the init and after every iteration, Lloyd
+    iterations with compute_centroids (ClusteringHelpers.cpp:101-172) and split_clusters, early stop when
+    the objective did not change (early_stop_threshold = 0, Clustering.cpp:360-377)."""
     x = np.asarray(x, dtype=np.float32)
     n, d = x.shape
     if n > k * max_points_per_centroid:
@@ -326,9 +337,11 @@ def kmeans(x, k, niter=25, seed=1234, max_points_per_centroid=256):
         n = x.shape[0]
     perm = rand_perm(n, seed + 1)
     cent = x[perm[:k]].copy()
+    if spherical:
+        cent = renorm_l2(cent)
     objs = []
-    for _ in range(niter):
-        D, I = knn_flat(x, cent, 1, METRIC_L2)
+    for it in range(niter):
+        D, I = knn_flat(x, cent, 1, metric)
         objs.append(np.float32(D.sum(dtype=np.float64)))
         a = I[:, 0]
         hassign = np.bincount(a, minlength=k).astype(np.float32)
@@ -340,7 +353,24 @@ def kmeans(x, k, niter=25, seed=1234, max_points_per_centroid=256):
         new[~nz] = 0
         cent = new
         split_clusters(d, k, n, hassign, cent)
+        if spherical:
+            cent = renorm_l2(cent)
+        if it > 0 and objs[-2] != 0 and abs(float(objs[-2]) - float(objs[-1])) / abs(float(objs[-2])) <= 0.0:
+            break
     return cent, np.array(objs, dtype=np.float32)
+
+
+def pq_train(x, M, niter=25, seed=1234, max_points_per_centroid=256):
+    """ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195): M independent
+    k-means (256 centroids) on the column slices, each a fresh Clustering(dsub, 256, cp)."""
+    x = np.asarray(x, dtype=np.float32)
+    n, d = x.shape
+    dsub = d // M
+    out = np.empty((M, 256, dsub), dtype=np.float32)
+    for m in range(M):
+        out[m], _ = kmeans(np.ascontiguousarray(x[:, m * dsub : (m + 1) * dsub]), 256, niter=niter, seed=seed,
+                           max_points_per_centroid=max_points_per_centroid)
+    return out
 
 
 # ----------------------------------------------------------------------------- comparison helpers

@@ -202,6 +202,16 @@ class _IVF(RefIndex):
         _ck(lib().ref_ivf_get_list(self.h, ctypes.c_int64(l), _p(codes, _u8), _p(ids, _i64)))
         return codes, ids
 
+    def add_entries(self, l, ids, codes):
+        """InvertedLists::add_entries: append pre-encoded vectors to list l (clone GPU -> CPU)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1)
+        assert codes.size == ids.size * self.code_size()
+        _ck(lib().ref_ivf_add_entries(self.h, ctypes.c_int64(l), ctypes.c_int64(ids.size), _p(ids, _i64), _p(codes, _u8)))
+
+    def set_is_trained(self, v=True):
+        lib().ref_ivf_set_is_trained(self.h, int(bool(v)))
+
     def quantizer_search(self, x, k):
         x = np.ascontiguousarray(x, dtype=np.float32)
         D = np.empty((x.shape[0], k), dtype=np.float32)
@@ -289,6 +299,25 @@ def kmeans(x, k, niter=25, seed=1234, max_points_per_centroid=256, min_points_pe
         )
     )
     return cent, obj, nsplit
+
+
+def pq_train(x, M, nbits=8, niter=25, seed=1234):
+    """faiss::ProductQuantizer::train on x [n, d]; returns centroids [M, 2^nbits, d/M]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, d = x.shape
+    out = np.empty((M, 1 << nbits, d // M), dtype=np.float32)
+    _ck(lib().ref_pq_train(int(d), int(M), int(nbits), ctypes.c_int64(n), _p(x, _f), int(niter), int(seed), _p(out, _f)))
+    return out
+
+
+def kmeans_spherical_ip(x, k, niter=10, seed=1234):
+    """faiss::Clustering with spherical=True over an IndexFlatIP (what GpuIndexIVF uses for METRIC_INNER_PRODUCT)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, d = x.shape
+    cent = np.empty((k, d), dtype=np.float32)
+    obj = np.zeros(niter, dtype=np.float32)
+    _ck(lib().ref_kmeans_spherical_ip(int(d), ctypes.c_int64(n), ctypes.c_int64(k), _p(x, _f), int(niter), int(seed), _p(cent, _f), _p(obj, _f)))
+    return cent, obj
 
 
 def merge_knn_results(all_D, all_I, metric=1):

@@ -13,6 +13,7 @@
 #include <faiss/IndexIVFPQ.h>
 #include <faiss/IndexShards.h>
 #include <faiss/impl/FaissException.h>
+#include <faiss/impl/ProductQuantizer.h>
 #include <faiss/invlists/InvertedLists.h>
 #include <faiss/utils/Heap.h>
 #include <faiss/utils/distances.h>
@@ -230,6 +231,51 @@ void ref_ivfpq_set_pq_niter(void* idx, int niter, int seed) {
 // faiss/impl/ProductQuantizer.cpp compute_codes (no residual) -- used to pin the PQ encoder
 int ref_pq_compute_codes(void* idx, const float* x, uint8_t* codes, int64_t n) {
     REF_TRY((faiss::IndexIVFPQ*)idx)->pq.compute_codes(x, codes, n);
+    REF_CATCH
+}
+
+// InvertedLists::add_entries (faiss/invlists/InvertedLists.h) -- bulk list load: the GPU -> CPU direction
+// of the cloner (index_gpu_to_cpu / GpuIndexIVFPQ::copyTo, faiss/gpu/GpuIndexIVFPQ.cu:160-217) so the CPU
+// baseline searches exactly the codes the GPU index holds
+int ref_ivf_add_entries(void* idx, int64_t l, int64_t n, const int64_t* ids, const uint8_t* codes) {
+    REF_TRY auto* p = (faiss::IndexIVF*)idx;
+    p->invlists->add_entries(l, n, ids, codes);
+    p->ntotal += n;
+    REF_CATCH
+}
+int ref_ivf_set_is_trained(void* idx, int v) {
+    ((faiss::Index*)idx)->is_trained = v != 0;
+    return 0;
+}
+int ref_ivf_set_parallel_mode(void* idx, int mode) {
+    ((faiss::IndexIVF*)idx)->parallel_mode = mode;
+    return 0;
+}
+// faiss/impl/ProductQuantizer.cpp:130-195 ProductQuantizer::train (Train_default: M independent k-means)
+int ref_pq_train(int d, int M, int nbits, int64_t n, const float* x, int niter, int seed, float* centroids_out) {
+    REF_TRY faiss::ProductQuantizer pq(d, M, nbits);
+    if (niter > 0)
+        pq.cp.niter = niter;
+    if (seed >= 0)
+        pq.cp.seed = seed;
+    pq.train(n, x);
+    memcpy(centroids_out, pq.centroids.data(), sizeof(float) * pq.centroids.size());
+    REF_CATCH
+}
+// Clustering with spherical = true and an inner-product assignment index (what GpuIndexIVF does for
+// METRIC_INNER_PRODUCT, faiss/gpu/GpuIndexIVF.cu:72-76; faiss/Clustering.cpp post_process_centroids)
+int ref_kmeans_spherical_ip(int d, int64_t n, int64_t k, const float* x, int niter, int seed, float* centroids_out, float* obj_out) {
+    REF_TRY faiss::ClusteringParameters cp;
+    cp.niter = niter;
+    cp.seed = seed;
+    cp.spherical = true;
+    faiss::Clustering clus(d, k, cp);
+    faiss::IndexFlatIP index(d);
+    clus.train(n, x, index);
+    memcpy(centroids_out, clus.centroids.data(), sizeof(float) * d * k);
+    for (size_t i = 0; i < clus.iteration_stats.size() && (int)i < niter; i++)
+        if (obj_out)
+            obj_out[i] = clus.iteration_stats[i].obj;
     REF_CATCH
 }
 

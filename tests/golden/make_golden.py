@@ -93,6 +93,19 @@ def main():
     D, I = ivf.search(xq, k)
     out["ivfflat_centroids"] = ivf.centroids()
     out["ivfflat_D"], out["ivfflat_I"] = D, I
+    # list membership (ids per list) so the oracle restatement can be pinned on the reference's own lists
+    out["ivfflat_lens"] = np.array([ivf.list_size(l) for l in range(nlist)])
+    out["ivfflat_ids"] = np.concatenate([ivf.get_list(l)[1] for l in range(nlist)])
+
+    # ---- ProductQuantizer::train (faiss/impl/ProductQuantizer.cpp:130-195): M independent k-means
+    xp = ref.float_rand(4000 * 16, 41).reshape(4000, 16)
+    out["pqtrain_centroids"] = ref.pq_train(xp, 4, 8, niter=6, seed=1234)
+    out["pqtrain_shape"] = np.array([4000, 16, 4, 6, 1234])
+
+    # ---- spherical k-means over an inner-product index (GpuIndexIVF's IP coarse training)
+    xs = ref.float_rand(3000 * 8, 51).reshape(3000, 8) - 0.5
+    cent, obj = ref.kmeans_spherical_ip(xs, 12, niter=6, seed=77)
+    out["kmeans_sph_centroids"], out["kmeans_sph_obj"] = cent, obj
 
     # ---- k-means (Clustering with a CPU IndexFlatL2)
     x = ref.float_rand(5000 * 8, 31).reshape(5000, 8)

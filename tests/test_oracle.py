@@ -101,6 +101,50 @@ def test_kmeans_oracle_vs_golden(golden):
     assert np.allclose(cent, golden["kmeans_sub_centroids"], rtol=1e-3, atol=1e-4)
 
 
+def test_ivfflat_search_oracle_vs_golden(golden):
+    """pins oracle_np.ivfflat_search on the reference's own IndexIVFFlat lists, centroids and results
+    (fixture minted by tests/golden/make_golden.py from oracle/_ref)"""
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    xb = o.float_rand(N * d, 21).reshape(N, d)
+    xq = o.float_rand(nq * d, 22).reshape(nq, d)
+    lens, ids_all = golden["ivfflat_lens"], golden["ivfflat_ids"]
+    assert lens.sum() == N
+    vecs, ids = [], []
+    i0 = 0
+    for n in lens:
+        li = ids_all[i0 : i0 + n]
+        ids.append(li)
+        vecs.append(xb[li])
+        i0 += n
+    D, I = o.ivfflat_search(xq, k, nprobe, golden["ivfflat_centroids"], vecs, ids, 1)
+    o.compare_lists(golden["ivfflat_D"], golden["ivfflat_I"], D, I, eps=1e-4, pct_max_diff1=0.01, pct_max_diffN=0.005)
+    # and the assignment that produced those lists is the oracle's coarse assignment (up to near-ties)
+    a = o.ivf_assign(xb, golden["ivfflat_centroids"], 1)
+    owner = np.empty(N, dtype=np.int64)
+    i0 = 0
+    for l, n in enumerate(lens):
+        owner[ids_all[i0 : i0 + n]] = l
+        i0 += n
+    assert (a != owner).sum() <= N * 0.002
+
+
+def test_pq_train_oracle_vs_golden(golden):
+    """ProductQuantizer::train (M independent k-means, same seeds) reproduced by the numpy restatement"""
+    n, d, M, niter, seed = [int(v) for v in golden["pqtrain_shape"]]
+    x = o.float_rand(n * d, 41).reshape(n, d)
+    c = o.pq_train(x, M, niter=niter, seed=seed)
+    assert np.allclose(c, golden["pqtrain_centroids"], rtol=1e-3, atol=1e-4)
+
+
+def test_kmeans_spherical_ip_oracle_vs_golden(golden):
+    """Clustering(spherical=True) over an inner-product index (GpuIndexIVF.cu:72-76 for METRIC_INNER_PRODUCT)"""
+    x = o.float_rand(3000 * 8, 51).reshape(3000, 8) - np.float32(0.5)
+    cent, obj = o.kmeans(x, 12, niter=6, seed=77, metric=0, spherical=True)
+    assert np.allclose(obj, golden["kmeans_sph_obj"][: len(obj)], rtol=1e-4)
+    assert np.allclose(cent, golden["kmeans_sph_centroids"], rtol=1e-3, atol=1e-4)
+    assert np.allclose(np.linalg.norm(cent, axis=1), 1.0, atol=1e-5)
+
+
 # ------------------------------------------------------------------ live checks against oracle/_ref
 def test_flat_vs_reference_live(ref):
     rs = np.random.RandomState(0)
