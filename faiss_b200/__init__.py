@@ -358,6 +358,12 @@ class GpuIndexIVF(Index):
             )
         )
 
+    def setListSizes(self, lens):
+        """exact capacity for every list in one relayout (call before the per-list setList of a bulk clone)"""
+        lens = np.ascontiguousarray(lens, dtype=np.int64)
+        assert lens.shape == (self.nlist,)
+        check(lib.faiss_GpuIndexIVF_setListSizes(self._h, _ptr(lens, _c_i64)))
+
     def setIsTrained(self, v=True):
         check(lib.faiss_GpuIndexIVF_set_is_trained(self._h, int(bool(v))))
 
@@ -508,6 +514,35 @@ def kmeans(res, x, k, niter=25, seed=1234, max_points_per_centroid=256, device=0
         )
     )
     return cent, obj
+
+
+def kmeans_ex(res, x, k, niter=25, seed=1234, max_points_per_centroid=256, metric=METRIC_L2, spherical=False, device=0):
+    """k-means with an assignment index of `metric` and ClusteringParameters::spherical."""
+    x = _as_f32(x)
+    n, d = x.shape
+    cent = np.empty((k, d), dtype=np.float32)
+    obj = np.zeros(niter, dtype=np.float32)
+    check(
+        lib.faiss_b200_kmeans_ex(
+            res._h, int(device), ctypes.c_size_t(d), ctypes.c_size_t(n), ctypes.c_size_t(k), _ptr(x, _c_f), int(niter), int(seed),
+            int(max_points_per_centroid), int(metric), int(bool(spherical)), _ptr(cent, _c_f), _ptr(obj, _c_f),
+        )
+    )
+    return cent, obj
+
+
+def pq_train(res, x, M, niter=25, seed=1234, device=0):
+    """faiss::ProductQuantizer::train (M independent 256-centroid k-means); returns [M, 256, d/M]."""
+    x = _as_f32(x)
+    n, d = x.shape
+    out = np.empty((M, 256, d // M), dtype=np.float32)
+    check(
+        lib.faiss_b200_pq_train(
+            res._h, int(device), ctypes.c_size_t(d), ctypes.c_size_t(M), ctypes.c_size_t(n), _ptr(x, _c_f), int(niter), int(seed),
+            _ptr(out, _c_f),
+        )
+    )
+    return out
 
 
 # ------------------------------------------------------------------ tier-2 seams (torch CUDA tensors)

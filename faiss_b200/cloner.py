@@ -66,6 +66,9 @@ def gpu_ivf_from_payload(res, payload, device=0):
     else:
         index = fb.GpuIndexIVFFlat(res, d, nlist, metric, device=device)
         index.setCoarseCentroids(payload["centroids"])
+    # all list lengths are known up front: ONE arena relayout with exact capacities, then plain copies
+    # (per-list growth would re-layout the whole arena once per list: quadratic in nlist)
+    index.setListSizes(np.array([len(payload["ids"][l]) for l in range(nlist)], dtype=np.int64))
     for l in range(nlist):
         if len(payload["ids"][l]):
             index.setList(l, payload["codes"][l], payload["ids"][l])

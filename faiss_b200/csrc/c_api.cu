@@ -383,6 +383,12 @@ int faiss_GpuIndexIVF_setList(FaissGpuIndex* p, size_t l, idx_t len, const uint8
     }
     CATCH_AND_HANDLE
 }
+int faiss_GpuIndexIVF_setListSizes(FaissGpuIndex* p, const idx_t* lens) {
+    try {
+        AS<GpuIndexIVF>(p, "GpuIndexIVF")->setListSizes(lens);
+    }
+    CATCH_AND_HANDLE
+}
 int faiss_GpuIndexIVF_set_is_trained(FaissGpuIndex* p, int v) {
     try {
         AS<GpuIndexIVF>(p, "GpuIndexIVF")->is_trained = v != 0;
@@ -553,6 +559,77 @@ int faiss_b200_kmeans(
             for (size_t i = 0; i < clus.iteration_stats.size() && (int)i < cp.niter; i++)
                 obj_out[i] = clus.iteration_stats[i].obj;
         }
+    }
+    CATCH_AND_HANDLE
+}
+
+int faiss_b200_kmeans_ex(
+        FaissStandardGpuResources* r,
+        int device,
+        size_t d,
+        size_t n,
+        size_t k,
+        const float* x,
+        int niter,
+        int seed,
+        int maxppc,
+        FaissMetricType metric,
+        int spherical,
+        float* centroids_out,
+        float* obj_out) {
+    try {
+        auto res = RES(r);
+        ClusteringParameters cp;
+        if (niter > 0)
+            cp.niter = niter;
+        if (seed >= 0)
+            cp.seed = seed;
+        if (maxppc > 0)
+            cp.max_points_per_centroid = maxppc;
+        cp.spherical = spherical != 0;
+        Clustering clus((int)d, (int)k, cp);
+        GpuIndexFlatConfig fc;
+        fc.device = device;
+        GpuIndexFlat index(res, (int)d, MT(metric), fc);
+        clus.train((idx_t)n, x, index);
+        memcpy(centroids_out, clus.centroids.data(), sizeof(float) * d * k);
+        if (obj_out) {
+            for (size_t i = 0; i < clus.iteration_stats.size() && (int)i < cp.niter; i++)
+                obj_out[i] = clus.iteration_stats[i].obj;
+        }
+    }
+    CATCH_AND_HANDLE
+}
+
+int faiss_b200_pq_train(
+        FaissStandardGpuResources* r,
+        int device,
+        size_t d,
+        size_t M,
+        size_t n,
+        const float* x,
+        int niter,
+        int seed,
+        float* centroids_out) {
+    try {
+        auto res = RES(r);
+        FB_THROW_IF_NOT_MSG(M > 0 && d % M == 0, "Number of sub-quantizers must be an integer divisor of the number of dimensions");
+        ClusteringParameters cp; // ProductQuantizer::cp defaults (faiss/impl/ProductQuantizer.h)
+        if (niter > 0)
+            cp.niter = niter;
+        if (seed >= 0)
+            cp.seed = seed;
+        DeviceScope scope(device);
+        res->initializeForDevice(device);
+        cudaStream_t stream = res->getDefaultStream(device);
+        GpuMemoryReservation hold;
+        const float* xd = x;
+        if (getDeviceForAddress(x) != device) {
+            hold = res->device_alloc(device, sizeof(float) * n * d, AllocType::Other);
+            CUDA_VERIFY(cudaMemcpyAsync(hold.data, x, sizeof(float) * n * d, cudaMemcpyDefault, stream));
+            xd = hold.as<float>();
+        }
+        trainProductQuantizer(res, device, (idx_t)n, xd, (int)d, (int)M, cp, centroids_out);
     }
     CATCH_AND_HANDLE
 }

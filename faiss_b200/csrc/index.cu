@@ -243,9 +243,18 @@ void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t*
         return;
     FB_THROW_IF_NOT_MSG(x && distances && labels, "null pointer passed to search");
     auto stream = stream_();
-    // query paging: bounded staging memory whatever n is (role of searchFromCpuPaged_,
-    // faiss/gpu/GpuIndex.cu:554-788)
-    const idx_t maxQ = std::max<idx_t>(1, std::min<idx_t>(idx_t(1) << 18, (idx_t)(minPagedSize_ / (sizeof(float) * d))));
+    // Query paging (role of searchFromCpuPaged_ / searchNonPaged_, faiss/gpu/GpuIndex.cu:554-788).
+    // minPagedSize_ is only the THRESHOLD above which host-resident queries are paged (as upstream:
+    // setMinPagingSize(0) means "always page", not "one query per page"); the page itself is a fixed
+    // byte budget (kSearchPageBytes) and is further bounded by k so that a page's result staging
+    // (k * 12 B per query, a few partial copies inside the kernels) stays within the temp arena.
+    constexpr size_t kSearchPageBytes = size_t(256) << 20;
+    const bool hostQueries = getDeviceForAddress(x) != config_.device;
+    idx_t maxQ = idx_t(1) << 18;
+    if (hostQueries && (size_t)n * d * sizeof(float) >= minPagedSize_)
+        maxQ = std::min<idx_t>(maxQ, (idx_t)(kSearchPageBytes / (sizeof(float) * d)));
+    maxQ = std::min<idx_t>(maxQ, (idx_t)((size_t(1) << 30) / ((size_t)k * 12 * 8)));
+    maxQ = std::max<idx_t>(maxQ, 1);
     for (idx_t i0 = 0; i0 < n; i0 += maxQ) {
         const idx_t nb = std::min(maxQ, n - i0);
         DeviceView<float> xv(resources_.get(), config_.device, x + (size_t)i0 * d, (size_t)nb * d, stream);
@@ -504,6 +513,8 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
             (long)nx,
             k);
     FB_THROW_IF_NOT_FMT((size_t)index.d == d, "Index dimension %d not the same as data dimension %d", index.d, (int)d);
+    // input centroids (hot start / frozen) are not part of this path; refuse instead of ignoring the flag
+    FB_THROW_IF_NOT_MSG(!frozen_centroids, "Clustering: frozen_centroids (input centroids) is not supported by faiss_b200");
     GpuResources* res = index.getResources().get();
     const int device = index.getDevice();
     DeviceScope scope(device);
@@ -576,10 +587,13 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
             gather_rows_int_kernel<<<(unsigned)k, std::min<int>(256, (int)d), 0, stream>>>(
                     x, pd.as<int>(), (int64_t)k, (int)d, cDev.as<float>());
             CUDA_CHECK_LAST();
+            runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
             CUDA_VERIFY(cudaStreamSynchronize(stream));
         }
         if (index.ntotal != 0)
             index.reset();
+        if (!index.is_trained)
+            index.train(k, cDev.as<float>());
         index.add(k, cDev.as<float>());
 
         float obj = 0;
@@ -628,8 +642,17 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
                        it, (now_ms() - t0) / 1000.0, t_search_tot / 1000.0, obj, imb, nsplit);
                 fflush(stdout);
             }
+            runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
             index.reset();
+            if (update_index)
+                index.train(k, cDev.as<float>());
             index.add(k, cDev.as<float>());
+            // early stop when the objective did not change (early_stop_threshold = 0, faiss/Clustering.cpp:360-377)
+            if (it > 0) {
+                const float prev = iteration_stats[iteration_stats.size() - 2].obj;
+                if (prev != 0 && std::fabs((double)prev - (double)obj) / std::fabs((double)prev) <= 0.0)
+                    break;
+            }
         }
         if (verbose)
             printf("\n");
@@ -773,6 +796,18 @@ void IvfLists::reserve(size_t totalVecs, cudaStream_t stream) {
         relayout_(cap, stream);
 }
 
+void IvfLists::reserveLists(const int64_t* lens, cudaStream_t stream) {
+    std::vector<int64_t> cap(nlist_);
+    bool grow = false;
+    for (int64_t l = 0; l < nlist_; l++) {
+        FB_THROW_IF_NOT_MSG(lens[l] >= 0 && lens[l] < (int64_t(1) << 31), "invalid inverted list length");
+        cap[l] = std::max<int64_t>(hCap_[l], lens[l]);
+        grow |= cap[l] > hCap_[l];
+    }
+    if (grow)
+        relayout_(cap, stream);
+}
+
 size_t IvfLists::reclaim(cudaStream_t stream) {
     size_t before = (size_t)arenaElems_ * (codeSize_ + sizeof(idx_t));
     std::vector<int64_t> cap(nlist_);
@@ -877,7 +912,9 @@ GpuIndexIVF::GpuIndexIVF(
         bool pqInterleaved)
         : GpuIndex(std::move(resources), dims, metric, 0, config), nlist(nlist_), ivfConfig_(config) {
     FB_THROW_IF_NOT_MSG(nlist > 0, "nlist must be > 0");
-    // faiss/gpu/GpuIndexIVF.cu:78-80
+    // faiss/gpu/GpuIndexIVF.cu:72-80: spherical k-means for inner product, 10 iterations
+    if (metric == METRIC_INNER_PRODUCT)
+        cp.spherical = true;
     cp.niter = 10;
     GpuIndexFlatConfig fc = config.flatConfig;
     fc.device = config.device;
@@ -915,6 +952,12 @@ std::vector<idx_t> GpuIndexIVF::getListIndices(idx_t listId) const {
 void GpuIndexIVF::reserveMemory(size_t numVecs) {
     DeviceScope scope(config_.device);
     lists_->reserve(numVecs, stream_());
+}
+
+void GpuIndexIVF::setListSizes(const idx_t* lens) {
+    DeviceScope scope(config_.device);
+    FB_THROW_IF_NOT_MSG(lens != nullptr, "null list-size array");
+    lists_->reserveLists(lens, stream_());
 }
 
 size_t GpuIndexIVF::reclaimMemory() {
@@ -1144,6 +1187,37 @@ void GpuIndexIVFPQ::getPQCentroids(float* out) const {
     CUDA_VERIFY(cudaStreamSynchronize(stream));
 }
 
+// ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195): M independent
+// k-means on the column slices, each with a fresh Clustering(dsub, ksub, cp).  x: device [n, d];
+// pqOut: host [M][256][dsub].
+void trainProductQuantizer(
+        std::shared_ptr<GpuResources> resources,
+        int device,
+        idx_t n,
+        const float* xDev,
+        int d,
+        int M,
+        const ClusteringParameters& cp,
+        float* pqOut) {
+    GpuResources* res = resources.get();
+    DeviceScope scope(device);
+    cudaStream_t stream = res->getDefaultStream(device);
+    const int ksub = 256, dsub = d / M;
+    auto slice = res->device_alloc(device, sizeof(float) * n * dsub, AllocType::Other);
+    GpuIndexFlatConfig fc;
+    fc.device = device;
+    GpuIndexFlatL2 pqIndex(resources, dsub, fc);
+    for (int m = 0; m < M; m++) {
+        slice_cols_kernel<<<(unsigned)ceil_div(n * dsub, 256), 256, 0, stream>>>(xDev, n, d, m * dsub, dsub, slice.as<float>());
+        CUDA_CHECK_LAST();
+        Clustering clus(dsub, ksub, cp);
+        clus.verbose = false;
+        pqIndex.reset();
+        clus.train(n, slice.as<float>(), pqIndex);
+        memcpy(pqOut + (size_t)m * ksub * dsub, clus.centroids.data(), sizeof(float) * ksub * dsub);
+    }
+}
+
 void GpuIndexIVFPQ::trainResidualQuantizer_(idx_t n, const float* xDev) {
     auto stream = stream_();
     GpuResources* res = resources_.get();
@@ -1174,23 +1248,8 @@ void GpuIndexIVFPQ::trainResidualQuantizer_(idx_t n, const float* xDev) {
     runCalcResidual(x, quantizer->vectorsDevice(), assign.as<idx_t>(), n, d, resid.as<float>(), stream);
     if (verbose)
         printf("training %d x %d product quantizer on %ld vectors in %dD\n", M_, ksub, (long)n, d);
-    // ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195): M independent
-    // k-means on the column slices, each with a fresh Clustering(dsub, ksub, cp)
     std::vector<float> pq((size_t)ksub * d);
-    auto slice = res->device_alloc(device, sizeof(float) * n * dsub, AllocType::Other);
-    GpuIndexFlatConfig fc;
-    fc.device = device;
-    GpuIndexFlatL2 pqIndex(resources_, dsub, fc);
-    for (int m = 0; m < M_; m++) {
-        slice_cols_kernel<<<(unsigned)ceil_div(n * dsub, 256), 256, 0, stream>>>(
-                resid.as<float>(), n, d, m * dsub, dsub, slice.as<float>());
-        CUDA_CHECK_LAST();
-        Clustering clus(dsub, ksub, pq_cp);
-        clus.verbose = false;
-        pqIndex.reset();
-        clus.train(n, slice.as<float>(), pqIndex);
-        memcpy(pq.data() + (size_t)m * ksub * dsub, clus.centroids.data(), sizeof(float) * ksub * dsub);
-    }
+    trainProductQuantizer(resources_, device, n, resid.as<float>(), d, M_, pq_cp, pq.data());
     setPQCentroids(pq.data());
 }
 

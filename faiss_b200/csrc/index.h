@@ -283,6 +283,17 @@ struct Clustering : ClusteringParameters {
     void train(idx_t n, const float* x, GpuIndexFlat& index);
 };
 
+// ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195); x device [n,d], pqOut host [M][256][d/M]
+void trainProductQuantizer(
+        std::shared_ptr<GpuResources> resources,
+        int device,
+        idx_t n,
+        const float* xDev,
+        int d,
+        int M,
+        const ClusteringParameters& cp,
+        float* pqOut);
+
 // helpers restated from the reference so that seeds reproduce its sampling decisions
 void rand_perm(int* perm, size_t n, int64_t seed);                   // faiss/utils/random.cpp:188-199
 int split_clusters(size_t d, size_t k, size_t n, float* hassign, float* centroids); // ClusteringHelpers.cpp:177-240
@@ -298,6 +309,8 @@ class IvfLists {
     ~IvfLists();
     void reset();
     void reserve(size_t totalVecs, cudaStream_t stream);
+    // exact per-list capacities in ONE relayout (bulk copyFrom: all list lengths are known up front)
+    void reserveLists(const int64_t* lens, cudaStream_t stream);
     // append n encoded rows (device pointers); assign[i] in [0,nlist) or -1 (skipped)
     // returns the number of rows actually stored
     idx_t append(idx_t n, const uint8_t* rowsDev, const idx_t* idsDev, const idx_t* assignDev, cudaStream_t stream);
@@ -394,6 +407,9 @@ class GpuIndexIVF : public GpuIndex {
     std::vector<uint8_t> getListVectorData(idx_t listId) const;
     std::vector<idx_t> getListIndices(idx_t listId) const;
     void reserveMemory(size_t numVecs);
+    // bulk-clone helper: exact capacity for every list in one arena relayout, before nlist x setList
+    // (the role of the per-list reserve in IVFBase::copyInvertedListsFrom, faiss/gpu/impl/IVFBase.cu:328-451)
+    void setListSizes(const idx_t* lens);
     size_t reclaimMemory();
     void reset() override;
     // install coarse centroids [nlist,d] (copyFrom of the CPU quantizer's xb)

@@ -162,6 +162,9 @@ void runKmeansFinalize(
         float* centroids /* in: previous, out: new (unchanged where count==0) */,
         cudaStream_t stream);
 
+// post_process_centroids (faiss/Clustering.cpp:35-45): spherical renormalisation and/or rounding to integers
+void runKmeansPostProcess(float* centroids, int64_t k, int d, bool spherical, bool intCentroids, cudaStream_t stream);
+
 // ---------------------------------------------------------------- ivf.cu
 // PQ encode: codes[i][m] = argmin_c || r_i[m*dsub:(m+1)*dsub] - pq[m][c] ||^2
 //   (role of IVFPQ::appendVectors_ per-subquantizer k=1 search, faiss/gpu/impl/IVFPQ.cu:129-257;

@@ -131,4 +131,40 @@ void runKmeansFinalize(
     CUDA_CHECK_LAST();
 }
 
+// post_process_centroids (faiss/Clustering.cpp:35-45): spherical -> fvec_renorm_L2 (rows with non-zero norm
+// scaled by 1/sqrtf(||row||^2), faiss/utils/distances.cpp:238-251); int_centroids -> roundf.  One warp per row.
+__global__ void kmeans_post_process_kernel(float* __restrict__ c, int64_t k, int d, int spherical, int intCentroids) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= k)
+        return;
+    float* r = c + row * d;
+    if (spherical) {
+        float acc = 0.f;
+        for (int j = lane_id(); j < d; j += 32)
+            acc = fmaf(r[j], r[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc += __shfl_xor_sync(kFullMask, acc, o);
+        if (acc > 0.f) {
+            const float inv = 1.0f / sqrtf(acc);
+            for (int j = lane_id(); j < d; j += 32)
+                r[j] *= inv;
+        }
+    }
+    if (intCentroids) {
+        __syncwarp();
+        for (int j = lane_id(); j < d; j += 32)
+            r[j] = roundf(r[j]);
+    }
+}
+
+void runKmeansPostProcess(float* centroids, int64_t k, int d, bool spherical, bool intCentroids, cudaStream_t stream) {
+    if (k == 0 || (!spherical && !intCentroids))
+        return;
+    const int warps = 8;
+    kmeans_post_process_kernel<<<(unsigned)ceil_div(k, warps), warps * 32, 0, stream>>>(
+            centroids, k, d, spherical ? 1 : 0, intCentroids ? 1 : 0);
+    CUDA_CHECK_LAST();
+}
+
 } // namespace fb200

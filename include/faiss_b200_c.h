@@ -119,6 +119,10 @@ FB200_API int faiss_GpuIndexIVF_getListIndices(const FaissGpuIndex* index, size_
 FB200_API int faiss_GpuIndexIVF_setCoarseCentroids(FaissGpuIndex* index, const float* centroids);
 FB200_API int faiss_GpuIndexIVF_getCoarseCentroids(const FaissGpuIndex* index, float* centroids_out);
 FB200_API int faiss_GpuIndexIVF_setList(FaissGpuIndex* index, size_t list_no, idx_t len, const uint8_t* codes, const idx_t* ids);
+/* bulk clone: exact capacity for all nlist lists in ONE arena relayout, to be called before the nlist
+   setList calls (lens: host, [nlist]) -- the per-list reserve of IVFBase::copyInvertedListsFrom
+   (faiss/gpu/impl/IVFBase.cu:328-451) */
+FB200_API int faiss_GpuIndexIVF_setListSizes(FaissGpuIndex* index, const idx_t* lens);
 FB200_API int faiss_GpuIndexIVF_set_is_trained(FaissGpuIndex* index, int v);
 /* c_api/IndexIVF_c.h:118 faiss_IndexIVF_search_preassigned */
 FB200_API int faiss_GpuIndexIVF_search_preassigned(const FaissGpuIndex* index, idx_t n, const float* x, idx_t k, const idx_t* assign, const float* centroid_dis, float* distances, idx_t* labels);
@@ -149,6 +153,13 @@ FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int
 /* ---- Clustering (c_api/Clustering_c.h faiss_kmeans_clustering; faiss/Clustering.cpp:60-380) ----
    Lloyd k-means with the training set resident on the device; x host or device. */
 FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, float* centroids_out /* host [k*d] */, float* obj_out /* host [niter] or NULL */);
+
+/* same with the assignment metric and ClusteringParameters::spherical (what GpuIndexIVF uses for
+   METRIC_INNER_PRODUCT, faiss/gpu/GpuIndexIVF.cu:72-76; post_process_centroids, faiss/Clustering.cpp:35-45) */
+FB200_API int faiss_b200_kmeans_ex(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, FaissMetricType metric, int spherical, float* centroids_out, float* obj_out);
+/* ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195): M independent 256-centroid
+   k-means on the column slices of x [n,d] (host or device); centroids_out host [M][256][d/M] */
+FB200_API int faiss_b200_pq_train(FaissStandardGpuResources* res, int device, size_t d, size_t M, size_t n, const float* x, int niter, int seed, float* centroids_out);
 
 /* ---- instrumentation (bench.py): kernels launched by this library so far; optional CUDA-event
    timing of a named kernel ("flat_tc") on its launching stream ---- */

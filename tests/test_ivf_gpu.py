@@ -288,3 +288,79 @@ def test_cloner_ivfpq_shards_equal_unsharded(res, shard_type):
     Ds, Is = shards.search(xq, k)
     assert np.allclose(Ds, D, rtol=1e-5, atol=0)
     o.compare_lists(D, I, Ds, Is, eps=1e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+
+
+def test_pq_train_matches_reference_fixture(res, golden):
+    """a16: GPU ProductQuantizer training (M independent k-means, same seeds and sampling) reproduces the
+    centroids of faiss::ProductQuantizer::train (fixture minted from oracle/_ref, faiss/impl/ProductQuantizer.cpp:130-195)"""
+    import faiss_b200 as fb
+
+    n, d, M, niter, seed = [int(v) for v in golden["pqtrain_shape"]]
+    x = o.float_rand(n * d, 41).reshape(n, d)
+    c = fb.pq_train(res, x, M, niter=niter, seed=seed)
+    g = golden["pqtrain_centroids"]
+    assert c.shape == g.shape
+    # same Lloyd trajectory: centroids agree to fp32 summation order
+    assert np.allclose(c, g, rtol=1e-3, atol=1e-4)
+
+
+def test_spherical_ip_kmeans_matches_reference_fixture(res, golden):
+    """GpuIndexIVF trains METRIC_INNER_PRODUCT coarse quantisers with spherical k-means
+    (faiss/gpu/GpuIndexIVF.cu:72-76): centroids renormalised after the init and after every iteration"""
+    import faiss_b200 as fb
+
+    x = o.float_rand(3000 * 8, 51).reshape(3000, 8) - np.float32(0.5)
+    cent, obj = fb.kmeans_ex(res, x, 12, niter=6, seed=77, metric=fb.METRIC_INNER_PRODUCT, spherical=True)
+    assert np.allclose(np.linalg.norm(cent, axis=1), 1.0, atol=1e-5)
+    assert np.allclose(obj, golden["kmeans_sph_obj"], rtol=1e-4)
+    assert np.allclose(cent, golden["kmeans_sph_centroids"], rtol=1e-3, atol=1e-4)
+    # and the IVF index itself: IP coarse centroids come out unit-norm
+    rs = np.random.RandomState(3)
+    xb = (rs.rand(6000, 16).astype(np.float32) - 0.5) * rs.rand(6000, 1).astype(np.float32) * 10
+    ivf = fb.GpuIndexIVFFlat(res, 16, 24, fb.METRIC_INNER_PRODUCT)
+    ivf.train(xb)
+    c = ivf.getCoarseCentroids()
+    assert np.allclose(np.linalg.norm(c, axis=1), 1.0, atol=1e-4)
+
+
+def test_ivfflat_golden_search(res, golden):
+    """a7 pinned on the reference's own IndexIVFFlat fixture: same centroids, device-side add, search"""
+    import faiss_b200 as fb
+
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    xb = o.float_rand(N * d, 21).reshape(N, d)
+    xq = o.float_rand(nq * d, 22).reshape(nq, d)
+    idx = fb.GpuIndexIVFFlat(res, d, nlist, fb.METRIC_L2)
+    idx.setCoarseCentroids(golden["ivfflat_centroids"])
+    idx.setIsTrained(True)
+    idx.add(xb)
+    idx.nprobe = nprobe
+    D, I = idx.search(xq, k)
+    o.compare_lists(golden["ivfflat_D"], golden["ivfflat_I"], D, I, eps=1e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+    # list membership equals the reference's up to assignment near-ties
+    lens, ids_all = golden["ivfflat_lens"], golden["ivfflat_ids"]
+    i0 = bad = 0
+    for l, n in enumerate(lens):
+        bad += len(set(idx.getListIndices(l).tolist()) ^ set(ids_all[i0 : i0 + n].tolist()))
+        i0 += n
+    assert bad <= N * 0.004
+
+
+def test_bulk_clone_single_relayout(res, golden):
+    """cloner: setListSizes reserves every list once; the clone equals the per-list path byte for byte"""
+    import faiss_b200 as fb
+    from faiss_b200 import cloner
+
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    codes, ids = _lists_from_golden(golden, "l2", M)
+    payload = {"d": d, "nlist": nlist, "metric": 1, "centroids": golden["ivfpq_l2_centroids"], "pq": golden["ivfpq_l2_pq"],
+               "codes": codes, "ids": ids}
+    idx = cloner.gpu_ivf_from_payload(res, payload)
+    assert idx.ntotal == N
+    for l in range(nlist):
+        assert np.array_equal(idx.getListVectorData(l), codes[l])
+        assert np.array_equal(idx.getListIndices(l), ids[l])
+    xq = o.float_rand(nq * d, 22).reshape(nq, d)
+    idx.nprobe = nprobe
+    D, I = idx.search(xq, k)
+    o.compare_lists(golden["ivfpq_l2_D"], golden["ivfpq_l2_I"], D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
