@@ -59,7 +59,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi
+    needs ~0.5 s to produce its first line, so it is started before the warm-up; samples are time-stamped
+    on arrival and only those inside [mark_begin, mark_end] (the timed region) are used -- widened to the
+    warm-up steps of the same workload if the timed region is shorter than one sampling period."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -67,12 +70,13 @@ class ClockSampler:
     def __init__(self, gpu_index=0):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (arrival time, text)
+        self.t_load = self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,7 +85,16 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_load(self):
+        self.t_load = time.time()
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
@@ -91,27 +104,35 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(t0, t1):
+            sm, smax, reasons, power = [], [], set(), []
+            for ts, ln in self.lines:
+                if t0 is not None and not (t0 <= ts <= t1 + 0.06):
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, reasons, power
+
+        window = "timed region"
+        sm, smax, reasons, power = parse(self.t_begin, self.t_end or time.time())
+        if len(sm) < 2 and self.t_load is not None:
+            window = "warm-up + timed region (same workload; the timed region is shorter than two sampling periods)"
+            sm, smax, reasons, power = parse(self.t_load, self.t_end or time.time())
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load" = samples in the upper half of the power range
-        thr = 0.5 * (max(power) + min(power))
-        load = [s for s, p in zip(sm, power) if p >= thr] or sm
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "lines_seen": len(self.lines)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power)), "window": window}
 
 
 def gen_rows(torch, device, r0, r1, d, n_total=None, seed0=1234):
@@ -661,23 +682,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.7)  # nvidia-smi start-up; outside every timed region
+    sampler.mark_load()
     for _ in range(max(warmup, 3)):
         step_device()
     barrier()
 
     # ---- timed region: device-resident inputs
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     fb.lib.faiss_b200_kernel_timing(1)
     l0 = fb.lib.faiss_b200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(steps):
         D, I = step_device()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1) / steps
     launches = fb.lib.faiss_b200_launch_count() - l0
     tc_ms = ctypes.c_double()

@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) flat_exact_kernel(
         unsigned char* base = listBase + perQuery * q;
         s.keys = reinterpret_cast<float*>(base);
         s.ids = reinterpret_cast<int*>(base + sizeof(float) * (LIST + C::BUF));
+        s.bkeys = s.keys + LIST;
+        s.bids = s.ids + LIST;
         s.LIST = LIST;
         s.BUF = C::BUF;
         s.k = k;

@@ -13,6 +13,7 @@
 // LUT and distances never touch HBM; the running top-k stays in shared memory (select.cuh).
 #include <cfloat>
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 #include "select.cuh"
@@ -55,7 +56,7 @@ __global__ void pq_scatter_interleaved_kernel(
     uint8_t* base = arenaCodes + ls * M;
     const int t = off & 31;
     for (int j = lane_id(); j < M; j += 32)
-        base[interleaved_pos(off, j, M)] = flat[i * M + ((j + t) % M)];
+        base[interleaved_pos(off, j, M)] = flat[i * M + ((j ^ t) & (M - 1))];
     if (lane_id() == 0)
         arenaIds[ls + off] = ids[i];
 }
@@ -66,7 +67,7 @@ __global__ void pq_list_to_interleaved_kernel(const uint8_t* __restrict__ flat, 
         return;
     const int64_t v = e / M;
     const int j = (int)(e - v * M);
-    dst[interleaved_pos(v, j, M)] = flat[v * M + ((j + (int)(v & 31)) % M)];
+    dst[interleaved_pos(v, j, M)] = flat[v * M + ((j ^ (int)(v & 31)) & (M - 1))];
 }
 
 __global__ void pq_list_from_interleaved_kernel(const uint8_t* __restrict__ src, int64_t len, int M, uint8_t* __restrict__ flat) {
@@ -75,54 +76,55 @@ __global__ void pq_list_from_interleaved_kernel(const uint8_t* __restrict__ src,
         return;
     const int64_t v = e / M;
     const int j = (int)(e - v * M);
-    flat[v * M + ((j + (int)(v & 31)) % M)] = src[interleaved_pos(v, j, M)];
+    flat[v * M + ((j ^ (int)(v & 31)) & (M - 1))] = src[interleaved_pos(v, j, M)];
 }
 
-// block-level merge of the per-warp lists into warp 0 + write-out.  List ids are arena positions;
-// the user labels are looked up only for the k survivors.
-template <typename IdT, int kWarps>
-__device__ void merge_and_write(
-        WarpTopK<IdT>& w,
-        int warp,
-        unsigned char* lists,
-        size_t perWarp,
-        int LIST,
-        int k,
-        const idx_t* __restrict__ arenaIds,
-        float* __restrict__ outD,
-        idx_t* __restrict__ outI) {
-    w.finish();
-    __syncthreads();
-    if (warp == 0) {
-        for (int ow = 1; ow < kWarps; ow++) {
-            const float* ok = reinterpret_cast<const float*>(lists + perWarp * ow);
-            const IdT* oi = reinterpret_cast<const IdT*>(lists + perWarp * ow + sizeof(float) * (LIST + kBuf));
-            for (int e0 = 0; e0 < k; e0 += 32) {
-                int e = e0 + lane_id();
-                bool valid = e < k;
-                float key = valid ? ok[e] : 0.f;
-                IdT id = valid ? oi[e] : 0;
-                valid = valid && id != IdLimits<IdT>::max();
-                if (!__any_sync(kFullMask, valid && key <= w.thr))
-                    break;
-                w.add(valid, key, id);
-            }
-        }
-        w.finish();
-        for (int j = lane_id(); j < k; j += 32) {
-            IdT id = w.q.ids[j];
-            bool ok2 = id != IdLimits<IdT>::max();
-            outD[j] = ok2 ? w.q.keys[j] : CUDART_INF_F;
-            outI[j] = ok2 ? arenaIds[id] : -1;
-        }
-    }
+// PRMT with the generic-mode selector (PTX prmt.b32): nibble n picks byte (n & 7) of {a (0-3), b (4-7)};
+// bit 3 of the nibble replicates that byte's sign bit instead (used below to produce zero bytes)
+template <unsigned SEL>
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+    return d;
 }
 
-// One CTA = one query x one chunk of its probes.  The per-warp top-k lists (and their thresholds)
-// live across the probes of the chunk, so the number of candidates that pass the threshold grows with
-// log(vectors scanned per CTA), not with the number of (query, probe) pairs; per probe only the LUT is
-// rebuilt.  Keys: L2 -> sum of LUT entries; IP -> -(q.centroid) - sum (coarse term folded in per probe).
-template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int LU>
+// ld.shared with the table's shared-window base folded into the instruction's immediate (LDS [R + imm]):
+// the PRMT result is then the complete address and a lookup is PRMT + LDS + FADD.
+template <int IMM>
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+// packed add of two fp32 pairs (Blackwell FADD2): {a0,a1} += {v0,v1}, each lane-wise add is a plain RN fp32 add
+__device__ __forceinline__ void add2(float& a0, float& a1, float v0, float v1) {
+    asm("{\n.reg .b64 ra, rv, rd;\nmov.b64 ra, {%0,%1};\nmov.b64 rv, {%2,%3};\nadd.rn.f32x2 rd, ra, rv;\nmov.b64 {%0,%1}, rd;\n}"
+        : "+f"(a0), "+f"(a1)
+        : "f"(v0), "f"(v1));
+}
+
+__global__ void smem_base_probe_kernel(unsigned* out) {
+    extern __shared__ __align__(16) unsigned char probe_raw[];
+    if (threadIdx.x == 0)
+        *out = (unsigned)__cvta_generic_to_shared(probe_raw);
+}
+
+// One CTA = one query x one chunk of its probes, kWarps warps.
+//
+//   * ONE top-k list per CTA (CtaTopK, select.cuh): every warp filters against the CTA-wide k-th key,
+//     survivors go to a small per-warp buffer, only the final half-merge runs under a CTA lock.  The list
+//     and its threshold live across all probes of the chunk.
+//   * LUT = [256 codes][2 buffers][32 slots] fp32 (64 KB): lane t looks byte j of its vector up in slot
+//     j ^ t (conflict-free: a permutation of the banks for every j), so a row is 128 B and TWO lookup tables
+//     fit where the rotated layout needed one.  L2 probes are therefore processed in PAIRS: barrier, build
+//     both tables, barrier, then the 16 warps walk the two lists as one stream of work units (units dealt
+//     round-robin across list boundaries) -- one barrier per probe instead of three, and the tail imbalance
+//     of a list is amortised over two.  IP (and any list-independent table) needs no barrier at all.
+//   * inner loop per lookup: PRMT (code byte -> row, packed per-lane slot byte -> column) + LDS + FADD.
+// Keys: L2 -> sum of LUT entries (+ ||x - c||^2 with precomputed tables); IP -> -(q.centroid) - sum.
+// SBASE: shared-window address of the dynamic shared memory when it is known on the host (probed once per
+// device), folded into the LDS immediate; -1 = generic (one extra IADD per lookup).  FADD2: packed adds.
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int SBASE, bool FADD2>
 __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
@@ -142,39 +144,39 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
         float* __restrict__ partD,
         idx_t* __restrict__ partI) {
     static_assert(!PRECOMP || IS_L2, "precomputed tables are an L2 decomposition");
+    static_assert((kWarps & (kWarps - 1)) == 0, "kWarps must be a power of two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kThreads = kWarps * 32;
+    constexpr int kU = M == 32 ? 4 : 8;      // groups per work unit: 4 KB of codes in flight per warp
+    constexpr int H = M / 16;                // 16-byte words per lane and group
+    constexpr int kEntriesPerThread = 256 * M / kThreads;
+    static_assert(256 * M % kThreads == 0, "LUT entries must divide evenly among the threads");
     const int q = blockIdx.y, chunk = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int dsub = d / M;
-    float* lut = reinterpret_cast<float*>(smem_raw);                 // [256][kLutSlots]
-    float* rs = lut + 256 * kLutSlots;                               // [d]
-    unsigned char* lists = reinterpret_cast<unsigned char*>(rs) + round_up(sizeof(float) * d, 16);
-    const size_t perWarp = SmemTopK<IdT>::bytes(LIST, kBuf);
+    float* lut = reinterpret_cast<float*>(smem_raw);                 // [256][2][32]
+    float* rs = lut + 256 * 64;                                      // [2][d] residuals of the probe pair / [d] query
+    int* ctl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(rs) + round_up(sizeof(float) * 2 * d, 16));
+    float* t1s = reinterpret_cast<float*>(ctl + 2);                  // [2] ||x - c||^2 of the pair (PRECOMP)
+    unsigned char* listMem = reinterpret_cast<unsigned char*>(ctl) + 16;
     float* oD = partD + ((int64_t)q * gridDim.x + chunk) * k;
     idx_t* oI = partI + ((int64_t)q * gridDim.x + chunk) * k;
 
-    WarpTopK<IdT> w;
-    unsigned char* mine = lists + perWarp * warp;
-    w.init(reinterpret_cast<float*>(mine), reinterpret_cast<IdT*>(mine + sizeof(float) * (LIST + kBuf)), LIST, kBuf, k);
-    const unsigned char* lutB = reinterpret_cast<const unsigned char*>(lut);
-    const unsigned lane4 = (unsigned)lane << 2;
+    CtaTopK<IdT> top;
+    top.init(listMem, ctl, LIST, k, kWarps);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(lut);
+    if (SBASE >= 0 && sbase != (unsigned)SBASE)
+        __trap(); // the host probed a different base: refuse to read the wrong addresses
+    // per-lane column bytes: byte b of P0 = ((lane ^ b) << 2); word w of a vector uses P0 ^ (w << 4 in every byte)
+    const unsigned t4 = (unsigned)lane << 2;
+    const unsigned P0 = t4 | ((t4 ^ 4u) << 8) | ((t4 ^ 8u) << 16) | ((t4 ^ 12u) << 24);
 
-    // kU groups (kU * 32 * M bytes) per warp iteration, all 128-bit loads issued before the first lookup;
-    // groups are dealt to the warps round-robin.  (Measured alternatives that did NOT help on B200, N=100M:
-    // a register double buffer for the next iteration's codes, 71 vs 66 ms; claiming groups from a shared
-    // counter to balance the per-probe barrier, 59.2 vs 57.7 ms; prefetch.global.L2 of the next chunk, 60.1.)
-    constexpr int kU = 4;
-    constexpr int kStride = kWarps * kU;
-    constexpr int kThreads = kWarps * 32;
-    constexpr int kEntriesPerThread = 256 * M / kThreads;
-    static_assert(256 * M % kThreads == 0, "LUT entries must divide evenly among the threads");
-
-    // direct LUT entry e = c*M + m from the vector r[d] in shared memory:
+    // direct LUT entry e = c*M + m from a vector r[d] in shared memory:
     //   L2: ||r|m - y||^2 (r = query - list centroid);  IP / PRECOMP term 3: <r|m, y> (r = query)
-    auto entry = [&](int e, bool l2form) {
+    auto entry = [&](const float* r, int e, bool l2form) {
         const int c = e / M, m = e - c * M;
         const float* cp = pqT + (size_t)e * dsub;
-        const float* rp = rs + m * dsub;
+        const float* rp = r + m * dsub;
         float acc = 0.f;
         if ((dsub & 3) == 0) {
             for (int j = 0; j < dsub; j += 4) {
@@ -196,126 +198,204 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
         } else {
             for (int j = 0; j < dsub; j++) {
                 if (l2form) {
-                    float df = rp[j] - cp[j];
+                    float df = rp[j] - __ldg(cp + j);
                     acc = fmaf(df, df, acc);
                 } else {
-                    acc = fmaf(rp[j], cp[j], acc);
+                    acc = fmaf(rp[j], __ldg(cp + j), acc);
                 }
             }
         }
         return acc;
     };
-    auto store = [&](int e, float val) {
+    // entry (c, m) of table `buf` -> slots m, m+M, ... (< 32) of the half-row
+    auto store = [&](int buf, int e, float val) {
         const int c = e / M, m = e - c * M;
 #pragma unroll
-        for (int s = 0; s < kLutSlots; s += M)
-            lut[c * kLutSlots + s + m] = val; // entry (c, m) -> slots m, m+M, ... (< 64), conflict-free
+        for (int s = 0; s < 32; s += M)
+            lut[c * 64 + buf * 32 + s + m] = val;
     };
 
-    // Query-only part, once per CTA.  IP: the whole LUT (-<x|m, y> does not depend on the list).
+    // one work unit: kU groups of 32 vectors of one list, looked up in table BUF
+    auto scanUnit = [&](auto bufTag, const uint8_t* codes, int ngroups, int g0, int len, int64_t ls, float add) {
+        constexpr int BUF = decltype(bufTag)::value;
+        uint4 cur[kU][H];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
+            const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+#pragma unroll
+            for (int h = 0; h < H; h++)
+                cur[u][h] = __ldg(gp + h * 32);
+        }
+        top.refresh();
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                const unsigned wds[4] = {cur[u][h].x, cur[u][h].y, cur[u][h].z, cur[u][h].w};
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    const unsigned P = P0 ^ ((unsigned)(h * 4 + wi) * 0x10101010u);
+                    // R = (code byte << 8) | column byte ; bytes 2, 3 = sign of a column byte (< 128) = 0
+                    unsigned R0 = prmt<0xCC04>(wds[wi], P);
+                    unsigned R1 = prmt<0xCC15>(wds[wi], P);
+                    unsigned R2 = prmt<0xCC26>(wds[wi], P);
+                    unsigned R3 = prmt<0xCC37>(wds[wi], P);
+                    constexpr int IMM = (SBASE >= 0 ? SBASE : 0) + BUF * 128;
+                    if (SBASE < 0) {
+                        R0 += sbase;
+                        R1 += sbase;
+                        R2 += sbase;
+                        R3 += sbase;
+                    }
+                    const float v0 = lds_f32<IMM>(R0), v1 = lds_f32<IMM>(R1), v2 = lds_f32<IMM>(R2), v3 = lds_f32<IMM>(R3);
+                    if (h == 0 && wi == 0) { // first word: start the two chains without adding to zero
+                        a0 = v0;
+                        a1 = v1;
+                    } else if (FADD2) {
+                        add2(a0, a1, v0, v1);
+                    } else {
+                        a0 += v0;
+                        a1 += v1;
+                    }
+                    if (FADD2) {
+                        add2(a0, a1, v2, v3);
+                    } else {
+                        a0 += v2;
+                        a1 += v3;
+                    }
+                }
+            }
+            const int v = (g0 + u) * 32 + lane;
+            const float key = (IS_L2 && !PRECOMP) ? a0 + a1 : (a0 + a1) + add;
+            top.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
+        }
+    };
+
+    // Query-only part, once per CTA.  IP: the whole table (-<x|m, y> does not depend on the list), buffer 0.
     // PRECOMP: term 3 = -2 <x|m, y> for this thread's entries, kept in registers across the probes.
     float t3[PRECOMP ? kEntriesPerThread : 1];
     if (!IS_L2 || PRECOMP) {
-        for (int i = threadIdx.x; i < d; i += blockDim.x)
+        for (int i = threadIdx.x; i < d; i += kThreads)
             rs[i] = Q[(int64_t)q * d + i];
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < kEntriesPerThread; i++) {
             const int e = threadIdx.x + i * kThreads;
-            const float dot = entry(e, false);
+            const float dot = entry(rs, e, false);
             if (PRECOMP)
                 t3[i] = -2.f * dot;
             else
-                store(e, -dot);
+                store(0, e, -dot);
         }
-        __syncthreads();
     }
+    __syncthreads(); // list initialised (and the IP table built)
 
-    const int pEnd = min(nprobe, (chunk + 1) * probesPerCta);
-    for (int p = chunk * probesPerCta; p < pEnd; p++) {
-        const idx_t l = probes[(int64_t)q * nprobe + p];
-        if (l < 0)
-            continue; // block-uniform
-        const int len = listLen[l];
-        const int64_t ls = listStart[l];
-        const uint8_t* codes = arenaCodes + ls * (int64_t)M;
-        const int ngroups = (len + 31) >> 5;
-        if (ngroups == 0)
-            continue;
-        float term1 = 0.f;
-        if (IS_L2) {
-            __syncthreads(); // every warp is done with the previous probe's LUT
-            if (PRECOMP) {
-                // LUT = T2[list] + term 3 (one coalesced load and one add per entry); term 1 = ||x - c||^2 is
-                // recomputed here by every warp identically, so the result does not depend on the caller's
-                // coarse distances (search == search_preassigned bit for bit)
-                const float* t2 = term2 + (size_t)l * 256 * M;
-                float v2[kEntriesPerThread];
+    const int pBegin = chunk * probesPerCta;
+    const int pEnd = min(nprobe, pBegin + probesPerCta);
+    int base = 0; // work units dealt so far (identical in every warp): unit i belongs to warp i % kWarps
+    if (IS_L2) {
+        for (int p0 = pBegin; p0 < pEnd; p0 += 2) {
+            idx_t l[2];
+            int len[2];
+            int64_t ls[2];
 #pragma unroll
-                for (int i = 0; i < kEntriesPerThread; i++)
-                    v2[i] = __ldg(t2 + threadIdx.x + i * kThreads);
-                float part = 0.f;
-                for (int i = lane; i < d; i += 32) {
-                    const float df = rs[i] - __ldg(coarse + l * d + i);
-                    part = fmaf(df, df, part);
+            for (int s = 0; s < 2; s++) {
+                l[s] = p0 + s < pEnd ? probes[(int64_t)q * nprobe + p0 + s] : -1;
+                len[s] = l[s] >= 0 ? listLen[l[s]] : 0;
+                ls[s] = l[s] >= 0 ? listStart[l[s]] : 0;
+            }
+            if (len[0] == 0 && len[1] == 0)
+                continue; // block-uniform
+            if (!PRECOMP) {
+                // only the table build reads rs, and the previous build finished before its closing barrier
+                for (int i = threadIdx.x; i < 2 * d; i += kThreads) {
+                    const int s = i >= d ? 1 : 0, j = i - s * d;
+                    const idx_t ll = s ? l[1] : l[0];
+                    rs[i] = ll >= 0 ? Q[(int64_t)q * d + j] - __ldg(coarse + ll * d + j) : 0.f;
                 }
+            }
+            __syncthreads(); // every warp is done with the previous pair's tables; residuals visible
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    part += __shfl_xor_sync(kFullMask, part, o);
-                term1 = part;
+            for (int s = 0; s < 2; s++) {
+                if (len[s] == 0)
+                    continue;
+                if (PRECOMP) {
+                    // table = T2[list] + term 3 (one coalesced load and one add per entry); term 1 = ||x - c||^2
+                    // is recomputed here, so the result does not depend on the caller's coarse distances
+                    // (search == search_preassigned bit for bit)
+                    const float* t2 = term2 + (size_t)l[s] * 256 * M;
+                    float v2[kEntriesPerThread];
 #pragma unroll
-                for (int i = 0; i < kEntriesPerThread; i++)
-                    store(threadIdx.x + i * kThreads, v2[i] + t3[i]);
-            } else {
-                for (int i = threadIdx.x; i < d; i += blockDim.x)
-                    rs[i] = Q[(int64_t)q * d + i] - coarse[l * d + i];
-                __syncthreads();
-#pragma unroll LU
-                for (int e = threadIdx.x; e < 256 * M; e += kThreads)
-                    store(e, entry(e, true));
+                    for (int i = 0; i < kEntriesPerThread; i++)
+                        v2[i] = __ldg(t2 + threadIdx.x + i * kThreads);
+                    if (warp == s) {
+                        float part = 0.f;
+                        for (int i = lane; i < d; i += 32) {
+                            const float df = rs[i] - __ldg(coarse + l[s] * d + i);
+                            part = fmaf(df, df, part);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            part += __shfl_xor_sync(kFullMask, part, o);
+                        if (lane == 0)
+                            t1s[s] = part;
+                    }
+#pragma unroll
+                    for (int i = 0; i < kEntriesPerThread; i++)
+                        store(s, threadIdx.x + i * kThreads, v2[i] + t3[i]);
+                } else {
+#pragma unroll 8
+                    for (int e = threadIdx.x; e < 256 * M; e += kThreads)
+                        store(s, e, entry(rs + s * d, e, true));
+                }
             }
             __syncthreads();
-        }
-
-        const float add = IS_L2 ? term1 : -coarseDis[(int64_t)q * nprobe + p];
-        for (int g0 = warp * kU; g0 < ngroups; g0 += kStride) {
-            uint4 cur[kU][M / 16];
 #pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
-                const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-#pragma unroll
-                for (int h = 0; h < M / 16; h++)
-                    cur[u][h] = __ldg(gp + h * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                for (int h = 0; h < M / 16; h++) {
-                    const unsigned wds[4] = {cur[u][h].x, cur[u][h].y, cur[u][h].z, cur[u][h].w};
-#pragma unroll
-                    for (int wi = 0; wi < 4; wi++) {
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            const int j = h * 16 + wi * 4 + b;
-                            // R = (byte << 8) | (lane << 2): LUT row of this code value + this lane's slot
-                            const unsigned R = __byte_perm(wds[wi], lane4, 0x6504 | (b << 4));
-                            const float val = *reinterpret_cast<const float*>(lutB + R + j * 4);
-                            if (j & 1)
-                                a1 += val;
-                            else
-                                a0 += val;
-                        }
-                    }
+            for (int s = 0; s < 2; s++) {
+                if (len[s] == 0)
+                    continue;
+                const uint8_t* codes = arenaCodes + ls[s] * (int64_t)M;
+                const int ngroups = (len[s] + 31) >> 5;
+                const int units = (ngroups + kU - 1) / kU;
+                const float add = PRECOMP ? t1s[s] : 0.f;
+                for (int u = (warp - base) & (kWarps - 1); u < units; u += kWarps) {
+                    if (s == 0)
+                        scanUnit(std::integral_constant<int, 0>{}, codes, ngroups, u * kU, len[s], ls[s], add);
+                    else
+                        scanUnit(std::integral_constant<int, 1>{}, codes, ngroups, u * kU, len[s], ls[s], add);
                 }
-                const int v = (g0 + u) * 32 + lane;
-                const float key = (IS_L2 && !PRECOMP) ? a0 + a1 : (a0 + a1) + add;
-                w.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
+                base += units;
             }
+        }
+    } else {
+        for (int p = pBegin; p < pEnd; p++) {
+            const idx_t l = probes[(int64_t)q * nprobe + p];
+            if (l < 0)
+                continue;
+            const int len = listLen[l];
+            if (len == 0)
+                continue;
+            const int64_t ls = listStart[l];
+            const uint8_t* codes = arenaCodes + ls * (int64_t)M;
+            const int ngroups = (len + 31) >> 5;
+            const int units = (ngroups + kU - 1) / kU;
+            const float add = -coarseDis[(int64_t)q * nprobe + p];
+            for (int u = (warp - base) & (kWarps - 1); u < units; u += kWarps)
+                scanUnit(std::integral_constant<int, 0>{}, codes, ngroups, u * kU, len, ls, add);
+            base += units;
         }
     }
-    merge_and_write<IdT, kWarps>(w, warp, lists, perWarp, LIST, k, arenaIds, oD, oI);
+    top.finish();
+    __syncthreads();
+    // the CTA's list -> partial result; list ids are arena positions, user labels only for the k survivors
+    for (int j = threadIdx.x; j < k; j += kThreads) {
+        const IdT id = top.q.ids[j];
+        const bool ok = id != IdLimits<IdT>::max();
+        oD[j] = ok ? top.q.keys[j] : CUDART_INF_F;
+        oI[j] = ok ? arenaIds[id] : -1;
+    }
 }
 
 // T2[l][e] (e = c*M + m) = ||y_e||^2 + 2 <centroid_l | m, y_e>
@@ -387,7 +467,7 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int LU>
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int SBASE, bool FADD2>
 static void launchScanV(
         dim3 grid,
         size_t smem,
@@ -409,7 +489,7 @@ static void launchScanV(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, PRECOMP, IdT, kWarps, LU>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, PRECOMP, IdT, kWarps, SBASE, FADD2>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
@@ -421,9 +501,42 @@ static void launchScanV(
 
 constexpr int kScanWarps = 16; // warps per CTA (8 -> 16: 66 -> 60 ms on the N=100M workload)
 
+// shared-window address of dynamic shared memory for this device (probed once); -1 if it is not the
+// value the fast instantiation was compiled for
+constexpr int kExpectedSmemBase = 1024; // sm_100: the first KB of a CTA's shared window is reserved
+static int probedSmemBase(int device, cudaStream_t stream) {
+    static int cache[64];
+    static bool have[64] = {};
+    if (device >= 0 && device < 64 && have[device])
+        return cache[device];
+    unsigned* out = nullptr;
+    unsigned h = 0xffffffffu;
+    CUDA_VERIFY(cudaMalloc(&out, sizeof(unsigned)));
+    CUDA_VERIFY(cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    smem_base_probe_kernel<<<1, 32, 100 * 1024, stream>>>(out);
+    CUDA_CHECK_LAST();
+    CUDA_VERIFY(cudaMemcpyAsync(&h, out, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    CUDA_VERIFY(cudaStreamSynchronize(stream));
+    CUDA_VERIFY(cudaFree(out));
+    if (device >= 0 && device < 64) {
+        cache[device] = (int)h;
+        have[device] = true;
+    }
+    return (int)h;
+}
+
 template <int M, bool IS_L2, bool PRECOMP, typename IdT, typename... Args>
-static void launchScan(Args... args) {
-    launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, 8>(args...);
+static void launchScan(int smemBase, Args... args) {
+    static const bool fadd2 = getenv("FB200_PQ_FADD2") ? atoi(getenv("FB200_PQ_FADD2")) != 0 : false;
+    static const bool generic = getenv("FB200_PQ_GENERIC_LDS") && atoi(getenv("FB200_PQ_GENERIC_LDS")) != 0;
+    if (smemBase == kExpectedSmemBase && !generic) {
+        if (fadd2)
+            launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, kExpectedSmemBase, true>(args...);
+        else
+            launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, kExpectedSmemBase, false>(args...);
+    } else {
+        launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, -1, false>(args...);
+    }
 }
 
 void runIvfPqScanInterleaved(
@@ -454,10 +567,11 @@ void runIvfPqScanInterleaved(
     FB_THROW_IF_NOT(ivfPqInterleavedSupported(M));
     const int LIST = std::max(64, next_pow2(k));
     const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
-    const size_t listBytes = wide ? SmemTopK<long long>::bytes(LIST, kBuf) : SmemTopK<int>::bytes(LIST, kBuf);
-    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * d, 16) + listBytes * kScanWarps;
+    const size_t listBytes = wide ? CtaTopK<long long>::bytes(LIST, kScanWarps) : CtaTopK<int>::bytes(LIST, kScanWarps);
+    size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * 2 * d, 16) + 16 + listBytes;
     FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
     const bool l2 = metric == METRIC_L2;
+    const int smemBase = probedSmemBase(device, stream);
     int probesPerCta = 1;
     const int chunks = ivfScanChunks(device, nq, nprobe, &probesPerCta);
     const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)chunks * k * 12)));
@@ -468,7 +582,7 @@ void runIvfPqScanInterleaved(
         dim3 grid((unsigned)chunks, (unsigned)nb);
 #define SCAN(M_, L2_, PRE_, ID_)                                                                                   \
     launchScan<M_, L2_, PRE_, ID_>(                                                                                \
-            grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
+            smemBase, grid, smem, stream, Q + q0 * d, d, probes + q0 * nprobe, coarseDis + q0 * nprobe, nprobe, probesPerCta, \
             coarseCentroids, pqCentroidsT, term2, listStart, listLen, arenaCodes, arenaIds, k, LIST,               \
             partD.as<float>(), partI.as<idx_t>())
 #define SCAN_ID(M_, L2_, PRE_)          \

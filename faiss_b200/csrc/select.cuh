@@ -56,6 +56,8 @@ template <typename IdT>
 struct SmemTopK {
     float* keys;
     IdT* ids;
+    float* bkeys; // pending buffer (keys + LIST unless the owner places it elsewhere)
+    IdT* bids;
     int LIST;
     int BUF;
     int k;
@@ -77,12 +79,12 @@ struct SmemTopK {
         return keys[k - 1];
     }
 
-    // warp-collective: sort buffer (n_pending valid entries), merge into list.
-    __device__ void flush(int n_pending) {
+    // warp-collective: sort the n_pending buffered entries ascending (bitonic, padded with sentinels to a
+    // power of two >= 32); returns the padded size
+    __device__ int sort_buffer(int n_pending) {
         const int lane = lane_id();
-        float* bk = keys + LIST;
-        IdT* bi = ids + LIST;
-        // size of the sub-buffer to sort: next pow2 >= n_pending (>= 32)
+        float* bk = bkeys;
+        IdT* bi = bids;
         int n = 32;
         while (n < n_pending)
             n <<= 1;
@@ -91,7 +93,6 @@ struct SmemTopK {
             bi[i] = IdLimits<IdT>::max();
         }
         __syncwarp();
-        // bitonic sort ascending of bk[0..n)
         for (int size = 2; size <= n; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int t = lane; t < (n >> 1); t += 32) {
@@ -112,6 +113,14 @@ struct SmemTopK {
                 __syncwarp();
             }
         }
+        return n;
+    }
+
+    // warp-collective: merge the sorted buffer (n entries, n <= LIST) into the sorted list
+    __device__ void merge_sorted_buffer(int n) {
+        const int lane = lane_id();
+        const float* bk = bkeys;
+        const IdT* bi = bids;
         // half-merge stage 0: L[LIST-1-j] = min(L[LIST-1-j], B[j])  (B ascending, L ascending)
         for (int j = lane; j < n; j += 32) {
             int a = LIST - 1 - j;
@@ -140,6 +149,11 @@ struct SmemTopK {
             __syncwarp();
         }
     }
+
+    // warp-collective: sort buffer (n_pending valid entries), merge into list.
+    __device__ void flush(int n_pending) {
+        merge_sorted_buffer(sort_buffer(n_pending));
+    }
 };
 
 // Warp-private streaming interface over SmemTopK: every lane offers one (key,id) per call.
@@ -152,6 +166,8 @@ struct WarpTopK {
     __device__ void init(float* keys, IdT* ids, int LIST, int BUF, int k) {
         q.keys = keys;
         q.ids = ids;
+        q.bkeys = keys + LIST;
+        q.bids = ids + LIST;
         q.LIST = LIST;
         q.BUF = BUF;
         q.k = k;
@@ -167,8 +183,8 @@ struct WarpTopK {
         if (m) {
             int pos = cnt + __popc(m & ((1u << lane_id()) - 1u));
             if (pass) {
-                q.keys[q.LIST + pos] = key;
-                q.ids[q.LIST + pos] = id;
+                q.bkeys[pos] = key;
+                q.bids[pos] = id;
             }
             cnt += __popc(m);
             if (cnt > q.BUF - 32) {
@@ -188,6 +204,136 @@ struct WarpTopK {
         }
         thr = q.threshold();
         __syncwarp();
+    }
+};
+
+// CTA-shared top-k: ONE sorted list per CTA plus a small pending buffer per warp.
+//
+// Why: with a private list per warp each warp's threshold only reflects the 1/W of the stream it has
+// seen, so W lists let ~W x more candidates through (k ln(n/(W k)) each) and every one of them costs a
+// shared-memory merge -- on the IVF-PQ scan (16 warps, k = 100) that was ~20 % of the kernel's
+// shared-memory wavefronts and instructions.  Here every warp filters against the CTA-wide k-th key
+// (`sthr`, possibly a little stale -- a stale threshold is only looser, never wrong: the k-th key of a
+// subset is an upper bound of the final k-th key), appends survivors to its own buffer with a ballot
+// compaction, sorts the buffer privately, and only the final half-merge into the shared list runs
+// under a CTA-wide lock.  The result is the exact top-k by (key, id) whatever the interleaving.
+template <typename IdT>
+struct CtaTopK {
+    static constexpr int BUF = 64;
+    SmemTopK<IdT> q; // q.keys/q.ids = shared list, q.bkeys/q.bids = this warp's buffer
+    int* lock;
+    volatile float* sthr;
+    int cnt;
+    float thr;
+
+    __host__ __device__ static size_t bytes(int LIST, int warps) {
+        return (size_t)LIST * (sizeof(float) + sizeof(IdT)) + (size_t)warps * BUF * (sizeof(float) + sizeof(IdT));
+    }
+
+    // block-collective: carve `mem` (bytes(LIST, warps), 16-byte aligned), initialise the shared list.
+    // ctl: two 4-byte words of shared memory (lock, threshold).  Caller must __syncthreads() afterwards.
+    __device__ void init(unsigned char* mem, int* ctl, int LIST, int k, int warps) {
+        q.keys = reinterpret_cast<float*>(mem);
+        q.ids = reinterpret_cast<IdT*>(mem + sizeof(float) * LIST);
+        unsigned char* bufs = mem + (size_t)LIST * (sizeof(float) + sizeof(IdT));
+        const int warp = threadIdx.x >> 5;
+        q.bkeys = reinterpret_cast<float*>(bufs) + warp * BUF;
+        q.bids = reinterpret_cast<IdT*>(bufs + sizeof(float) * warps * BUF) + warp * BUF;
+        q.LIST = LIST;
+        q.BUF = BUF;
+        q.k = k;
+        lock = ctl;
+        sthr = reinterpret_cast<volatile float*>(ctl + 1);
+        for (int i = threadIdx.x; i < LIST; i += blockDim.x) {
+            q.keys[i] = CUDART_INF_F;
+            q.ids[i] = IdLimits<IdT>::max();
+        }
+        if (threadIdx.x == 0) {
+            ctl[0] = 0;
+            *sthr = CUDART_INF_F;
+        }
+        cnt = 0;
+        thr = CUDART_INF_F;
+    }
+
+    __device__ __forceinline__ void refresh() {
+        thr = *sthr;
+    }
+
+    // warp-collective; `valid` false lanes offer nothing.  NaN keys never pass.
+    __device__ __forceinline__ void add(bool valid, float key, IdT id) {
+        const bool pass = valid && (key <= thr);
+        const unsigned m = __ballot_sync(kFullMask, pass);
+        if (m) {
+            const int pos = cnt + __popc(m & ((1u << lane_id()) - 1u));
+            if (pass) {
+                q.bkeys[pos] = key;
+                q.bids[pos] = id;
+            }
+            cnt += __popc(m);
+            if (cnt > BUF - 32)
+                drain();
+        }
+    }
+
+    // drop buffered entries that no longer beat the (refreshed) threshold
+    __device__ void compact() {
+        const int lane = lane_id();
+        const bool h0 = lane < cnt, h1 = lane + 32 < cnt;
+        const float k0 = h0 ? q.bkeys[lane] : 0.f, k1 = h1 ? q.bkeys[lane + 32] : 0.f;
+        const IdT i0 = h0 ? q.bids[lane] : 0, i1 = h1 ? q.bids[lane + 32] : 0;
+        const bool p0 = h0 && k0 <= thr, p1 = h1 && k1 <= thr;
+        const unsigned m0 = __ballot_sync(kFullMask, p0), m1 = __ballot_sync(kFullMask, p1);
+        const unsigned lt = (1u << lane) - 1u;
+        if (p0) {
+            const int pos = __popc(m0 & lt);
+            q.bkeys[pos] = k0;
+            q.bids[pos] = i0;
+        }
+        if (p1) {
+            const int pos = __popc(m0) + __popc(m1 & lt);
+            q.bkeys[pos] = k1;
+            q.bids[pos] = i1;
+        }
+        cnt = __popc(m0) + __popc(m1);
+        __syncwarp();
+    }
+
+    // warp-collective: fold the pending buffer into the shared list
+    __device__ void drain(bool force = false) {
+        __syncwarp();
+        const float t = *sthr;
+        if (t < thr) { // somebody tightened the threshold since we filtered: re-filter first
+            thr = t;
+            compact();
+            if (!force && cnt <= BUF - 32)
+                return;
+        }
+        if (cnt == 0)
+            return;
+        const int n = q.sort_buffer(cnt); // private: no lock needed
+        if (lane_id() == 0) {
+            while (atomicCAS(lock, 0, 1) != 0)
+                __nanosleep(32);
+        }
+        __syncwarp();
+        __threadfence_block();
+        q.merge_sorted_buffer(n);
+        const float nt = q.keys[q.k - 1];
+        __syncwarp();
+        if (lane_id() == 0)
+            *sthr = nt;
+        __threadfence_block();
+        __syncwarp();
+        if (lane_id() == 0)
+            atomicExch(lock, 0);
+        cnt = 0;
+        thr = nt;
+    }
+
+    __device__ void finish() {
+        if (cnt > 0)
+            drain(true);
     }
 };
 

@@ -30,6 +30,20 @@ for n, r in enumerate(data[:maxn]):
     for key, label in want:
         if key in col and r[col[key]] != "":
             print("  %-34s %s %s" % (label, r[col[key]], units[col[key]]))
+    pipes = []
+    for h, i in col.items():
+        if (h.startswith("sm__inst_executed_pipe_") or h.startswith("sm__pipe_")) and h.endswith("pct_of_peak_sustained_active"):
+            try:
+                pipes.append((float(r[i]), h.replace(".avg.pct_of_peak_sustained_active", "").replace(".sum.pct_of_peak_sustained_active", "")))
+            except ValueError:
+                pass
+    pipes.sort(reverse=True)
+    if pipes:
+        print("  busiest pipes (% of peak, active):  " + ", ".join("%s %.1f" % (n2, v) for v, n2 in pipes[:8]))
+    for key in ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+                "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "smsp__cycles_active.avg"):
+        if key in col and r[col[key]] != "":
+            print("  %-34s %s %s" % (key[:34], r[col[key]], units[col[key]]))
     stalls = []
     for h, i in col.items():
         if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
