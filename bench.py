@@ -637,9 +637,15 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     import faiss_b200 as fb
-    from faiss_b200.distributed import ShardedSearcher, shard_bounds
+    from faiss_b200.distributed import shard_bounds
 
     res = fb.StandardGpuResources()
+    if world > 1:
+        # the NCCL communicator of the search path is owned by the library's resources object; torch.distributed
+        # only hands the 128-byte id to the other ranks (plumbing) and provides the barrier around the timed region
+        ids = [fb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=device)
+        res.ncclInitRank(local_rank, world, rank, ids[0])
     # order the library's work on torch's current stream so torch CUDA events bracket it
     stream = torch.cuda.current_stream(device)
     res.setDefaultStream(local_rank, stream.cuda_stream)
@@ -658,24 +664,16 @@ def main():
     torch.cuda.synchronize()
     log("[rank %d] shard rows [%d,%d) built in %.1f s" % (rank, r0, r1, time.time() - t0))
 
-    searcher = None
-    if world > 1:
-        searcher = ShardedSearcher(lambda q, k: index.search(q, k), r1 - r0, fb.METRIC_L2, res=res, device=local_rank)
+    # world > 1: IndexShards with one shard per rank behind the C ABI (faiss_DistributedIndexShards): pooled
+    # thresholds per round, ONE grouped ncclAllGather of the per-shard [nq,k] blocks, device merge
+    searcher = fb.DistributedIndexShards(res, index, successive_ids=True) if world > 1 else index
+    assert searcher.ntotal == N_TOTAL
 
     def step_device():
-        if searcher is not None:
-            return searcher.search(xq, K)
-        return index.search(xq, K)
+        return searcher.search(xq, K)
 
     def step_e2e():
-        if searcher is not None:
-            q = xq_pin.to(device, non_blocking=True)
-            D, I = searcher.search(q, K)
-            D_pin.copy_(D, non_blocking=True)
-            I_pin.copy_(I, non_blocking=True)
-            torch.cuda.synchronize()
-        else:
-            index.search(xq_pin.numpy(), K, D=D_pin.numpy(), I=I_pin.numpy())  # H2D + search + D2H inside
+        searcher.search(xq_pin.numpy(), K, D=D_pin.numpy(), I=I_pin.numpy())  # H2D + search + D2H inside
 
     def barrier():
         if dist is not None:
@@ -708,6 +706,9 @@ def main():
     tc_ms = ctypes.c_double()
     tc_n = ctypes.c_int()
     fb.lib.faiss_b200_kernel_timing_collect(b"flat_tc", ctypes.byref(tc_ms), ctypes.byref(tc_n))
+    ex_ms, mg_ms, ex_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+    fb.lib.faiss_b200_kernel_timing_collect(b"shards_exchange", ctypes.byref(ex_ms), ctypes.byref(ex_n))
+    fb.lib.faiss_b200_kernel_timing_collect(b"shards_merge", ctypes.byref(mg_ms), ctypes.byref(ex_n))
     fb.lib.faiss_b200_kernel_timing(0)
     clocks = sampler.stop() if rank == 0 else None
     info = index.lastSearchInfo()
@@ -763,6 +764,9 @@ def main():
                        "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 12},
                "gpu_launches": int(launches), "roofline": roof,
                "search_info": info}
+        if world > 1:
+            out["collective_ms"] = ex_ms.value / steps  # rank 0's all-gather (includes waiting for the slowest rank)
+            out["merge_ms"] = mg_ms.value / steps
         # ---- parity of the timed step's result (outside the timed region)
         if not args.no_parity:
             try:

@@ -110,6 +110,23 @@ class StandardGpuResources:
         raw = json.loads(buf.value.decode())
         return {int(d): {k: tuple(v) for k, v in m.items()} for d, m in raw.items()}
 
+    # -- NCCL communicator ownership
+    def ncclInitAll(self, devices):
+        """all listed devices of this process in one clique (rank i = devices[i])"""
+        arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        check(lib.faiss_StandardGpuResources_ncclInitAll(self._h, len(devices), arr))
+
+    def ncclInitRank(self, device, nranks, rank, unique_id):
+        """this process = rank `rank` of `nranks`; unique_id: the 128 bytes of nccl_unique_id() from one rank"""
+        unique_id = bytes(unique_id)
+        assert len(unique_id) == 128
+        check(lib.faiss_StandardGpuResources_ncclInitRank(self._h, int(device), int(nranks), int(rank), unique_id))
+
+    def ncclRank(self, device):
+        r, n = ctypes.c_int(), ctypes.c_int()
+        check(lib.faiss_StandardGpuResources_ncclRank(self._h, int(device), ctypes.byref(r), ctypes.byref(n)))
+        return r.value, n.value
+
     def getTempMemoryAvailable(self, device):
         out = ctypes.c_size_t()
         check(lib.faiss_StandardGpuResources_getTempMemoryAvailable(self._h, int(device), ctypes.byref(out)))
@@ -484,12 +501,52 @@ class IndexShards(Index):
     def count(self):
         return len(self._shards)
 
+    def lastSearchPath(self):
+        """'nccl' if the last search ran per-device threads + ncclAllGather + device merge, 'host' for the
+        reference's thread-per-shard + host merge"""
+        return {0: "host", 1: "nccl"}.get(lib.faiss_IndexShards_lastSearchPath(self._h), "?")
+
     def __del__(self):
         # free the meta index before the shards it points to
         if getattr(self, "_h", None) and lib is not None:
             lib.faiss_Index_free(self._h)
             self._h = None
         self._shards = []
+
+
+def nccl_unique_id():
+    """128 bytes to hand to every rank's StandardGpuResources.ncclInitRank (ncclGetUniqueId)."""
+    buf = ctypes.create_string_buffer(128)
+    check(lib.faiss_b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+class DistributedIndexShards(Index):
+    """IndexShards with one shard per NCCL rank (faiss/IndexShards.cpp:197-264 semantics; one grouped
+    all-gather + device merge; Flat shards pool their thresholds).  `search` is a collective call."""
+
+    def __init__(self, res, local, successive_ids=True):
+        super().__init__()
+        self._keep.append(res)
+        self._local = local
+        check(lib.faiss_DistributedIndexShards_new(ctypes.byref(self._h), res._h, local._h, int(bool(successive_ids))))
+
+    def _resources(self):
+        return [r for r in self._keep if isinstance(r, StandardGpuResources)]
+
+    def sync(self):
+        check(lib.faiss_DistributedIndexShards_sync(self._h))
+
+    def info(self):
+        r, n, o = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        check(lib.faiss_DistributedIndexShards_info(self._h, ctypes.byref(r), ctypes.byref(n), ctypes.byref(o)))
+        return {"rank": r.value, "world": n.value, "id_offset": o.value}
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.faiss_Index_free(self._h)
+            self._h = None
+        self._local = None
 
 
 def kmeans(res, x, k, niter=25, seed=1234, max_points_per_centroid=256, device=0):

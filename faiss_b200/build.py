@@ -66,7 +66,7 @@ def build(jobs=None, force=False, verbose=True):
         with ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 4)) as ex:
             list(ex.map(cc, todo))
     if todo or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-Xlinker", "-z", "-Xlinker", "defs"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-Xlinker", "-z", "-Xlinker", "defs"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

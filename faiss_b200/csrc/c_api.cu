@@ -3,6 +3,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "comm.h"
 #include "faiss_b200_c.h"
 #include "index.h"
 
@@ -525,6 +526,97 @@ void faiss_IndexShards_set_successive_ids(FaissIndexShards* p, int v) {
     auto* s = p ? dynamic_cast<IndexShards*>(p->index) : nullptr;
     if (s)
         s->successive_ids = v != 0;
+}
+
+// ---------------------------------------------------------------- NCCL communicator ownership + sharded search
+int faiss_b200_nccl_unique_id(char* out128) {
+    try {
+        FB_THROW_IF_NOT_MSG(out128 != nullptr, "null output buffer");
+        auto id = Communicator::uniqueId();
+        memcpy(out128, id.data(), id.size());
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_ncclInitRank(FaissStandardGpuResources* r, int device, int nranks, int rank, const char* id128) {
+    try {
+        FB_THROW_IF_NOT_MSG(id128 != nullptr, "null unique id");
+        RES(r)->ncclInitRank(device, nranks, rank, id128);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_ncclInitAll(FaissStandardGpuResources* r, int ndev, const int* devices) {
+    try {
+        FB_THROW_IF_NOT_MSG(ndev > 0 && devices != nullptr, "no devices");
+        RES(r)->ncclInitAll(std::vector<int>(devices, devices + ndev));
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_StandardGpuResources_ncclRank(FaissStandardGpuResources* r, int device, int* rank, int* nranks) {
+    try {
+        auto c = RES(r)->getCommunicator(device);
+        FB_THROW_IF_NOT_MSG(c != nullptr, "no communicator for this device");
+        if (rank)
+            *rank = c->rank();
+        if (nranks)
+            *nranks = c->size();
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_IndexShards_lastSearchPath(const FaissIndexShards* p) {
+    try {
+        return AS<IndexShards>(p, "IndexShards")->lastSearchPath;
+    } catch (...) {
+        return -1;
+    }
+}
+int faiss_DistributedIndexShards_new(FaissIndexShards** p, FaissStandardGpuResources* r, FaissGpuIndex* local, int successive_ids) {
+    try {
+        auto res = RES(r);
+        auto* h = new FaissIndex_H{nullptr, res};
+        try {
+            h->index = new DistributedIndexShards(res, AS<GpuIndex>(local, "GpuIndex"), successive_ids != 0);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_DistributedIndexShards_sync(FaissIndexShards* p) {
+    try {
+        AS<DistributedIndexShards>(p, "DistributedIndexShards")->syncWithSubIndexes();
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_DistributedIndexShards_info(const FaissIndexShards* p, int* rank, int* nranks, idx_t* id_offset) {
+    try {
+        auto* s = AS<DistributedIndexShards>(p, "DistributedIndexShards");
+        if (rank)
+            *rank = s->rank();
+        if (nranks)
+            *nranks = s->worldSize();
+        if (id_offset)
+            *id_offset = s->idOffset();
+    }
+    CATCH_AND_HANDLE
+}
+int b200_shards_search(
+        FaissStandardGpuResources* r,
+        FaissGpuIndex* local_shard,
+        int successive_ids,
+        idx_t n,
+        const float* x,
+        idx_t k,
+        float* distances,
+        idx_t* labels) {
+    try {
+        // one-shot form (re-reads every shard's size first: one tiny extra collective); hold a
+        // DistributedIndexShards for repeated searches
+        DistributedIndexShards s(RES(r), AS<GpuIndex>(local_shard, "GpuIndex"), successive_ids != 0);
+        s.search(n, x, k, distances, labels);
+    }
+    CATCH_AND_HANDLE
 }
 
 // ---------------------------------------------------------------- clustering

@@ -298,6 +298,8 @@ __global__ void merge_topk_kernel(
         int LIST,
         int isL2,
         int64_t idBase,
+        int64_t rowStride,  // elements between consecutive rows of one list
+        int64_t listStride, // elements between consecutive lists of one row
         float* __restrict__ outD,
         idx_t* __restrict__ outI) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -312,21 +314,23 @@ __global__ void merge_topk_kernel(
     w.init(reinterpret_cast<float*>(base), reinterpret_cast<long long*>(base + sizeof(float) * (LIST + BUF)), LIST, BUF, k);
 
     const int64_t total = (int64_t)nlists * kin;
-    const float* D = inD + row * total;
-    const idx_t* I = inI + row * total;
+    const float* D = inD + row * rowStride;
+    const idx_t* I = inI + row * rowStride;
     for (int64_t e0 = 0; e0 < total; e0 += 32) {
         int64_t e = e0 + lane;
         bool valid = e < total;
         float key = 0.f;
         long long id = -1;
         if (valid) {
-            id = I[e];
-            key = D[e];
+            const int64_t l = e / kin;
+            const int64_t at = l * listStride + (e - l * kin);
+            id = I[at];
+            key = D[at];
             if (id < 0) {
                 valid = false;
             } else {
                 if (idOffsets)
-                    id += idOffsets[e / kin];
+                    id += idOffsets[l];
                 if (!IN_KEYSPACE && !isL2)
                     key = -key;
             }
@@ -361,7 +365,8 @@ static void launchMerge(
         int64_t idBase,
         float* outD,
         idx_t* outI,
-        cudaStream_t stream) {
+        cudaStream_t stream,
+        bool listMajor = false) {
     if (rows == 0)
         return;
     int LIST = listSizeFor(k, 64);
@@ -371,7 +376,8 @@ static void launchMerge(
     auto kern = inKeyspace ? merge_topk_kernel<true> : merge_topk_kernel<false>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)ceil_div(rows, warps), warps * 32, smem, stream>>>(
-            inD, inI, rows, nlists, kin, idOffsets, k, LIST, metric == METRIC_L2 ? 1 : 0, idBase, outD, outI);
+            inD, inI, rows, nlists, kin, idOffsets, k, LIST, metric == METRIC_L2 ? 1 : 0, idBase,
+            listMajor ? (int64_t)kin : (int64_t)nlists * kin, listMajor ? rows * (int64_t)kin : (int64_t)kin, outD, outI);
     CUDA_CHECK_LAST();
 }
 
@@ -388,6 +394,22 @@ void runMergeTopK(
         idx_t* outI,
         cudaStream_t stream) {
     launchMerge(false, inD, inI, rows, nlists, kin, idOffsets, k, metric, 0, outD, outI, stream);
+}
+
+// inputs laid out [nlists][rows][kin] -- exactly what an all-gather of per-shard [rows][kin] results produces
+void runMergeTopKListMajor(
+        const float* inD,
+        const idx_t* inI,
+        int64_t rows,
+        int nlists,
+        int kin,
+        const idx_t* idOffsets,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream) {
+    launchMerge(false, inD, inI, rows, nlists, kin, idOffsets, k, metric, 0, outD, outI, stream, true);
 }
 
 // internal: inputs already in key space (IP negated)

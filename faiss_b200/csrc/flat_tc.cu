@@ -35,6 +35,7 @@
 #include <mutex>
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 #include "select.cuh"
 #include "tc_ptx.cuh"
@@ -192,7 +193,9 @@ __global__ void tc_select_kernel(
         float* __restrict__ baseKey, // [nq][LIST]
         int* __restrict__ baseId,    // [nq][LIST]
         float* __restrict__ thr,
-        int* __restrict__ flags) {
+        int* __restrict__ flags,
+        float* __restrict__ contrib, // sharded search: [2][nq] certified lower bounds for the cross-rank threshold (or null)
+        int kFrac) {                 // ceil(k / number of shards)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = lane_id();
@@ -206,10 +209,15 @@ __global__ void tc_select_kernel(
     // note: selection keeps the LIST best (k = LIST for the queue threshold)
     const float* bk = baseKey + (int64_t)q * LIST;
     const int* bi = baseId + (int64_t)q * LIST;
-    // the base list is already sorted (sentinels last): adopt it as the queue's list
+    // the base list is already sorted (sentinels last): adopt it as the queue's list.  The threshold may
+    // have been raised since the list was written (cross-rank pooling): entries it now excludes form a
+    // suffix of the sorted list and are dropped here.
+    const float thrNow = thr[q];
     for (int e0 = 0; e0 < LIST; e0 += 32) {
-        w.q.keys[e0 + lane] = bk[e0 + lane];
-        w.q.ids[e0 + lane] = bi[e0 + lane];
+        const float kk = bk[e0 + lane];
+        const bool keep = -kk > thrNow;
+        w.q.keys[e0 + lane] = keep ? kk : CUDART_INF_F;
+        w.q.ids[e0 + lane] = keep ? bi[e0 + lane] : IdLimits<int>::max();
     }
     __syncwarp();
     w.thr = w.q.threshold();
@@ -270,9 +278,31 @@ __global__ void tc_select_kernel(
         oi[j] = keep ? id : IdLimits<int>::max();
     }
     if (lane == 0) {
-        thr[q] = t;
+        thr[q] = fmaxf(t, thrNow);
         if (overflow)
             flags[q] = 1;
+        if (contrib) {
+            // certified lower bounds of true scores: >= k rows of this shard score at least c0, >= kFrac rows at
+            // least c1.  Across S shards: max_r c0 and min_r c1 (S * kFrac >= k rows) both bound the global k-th.
+            const float e = eps[q];
+            const float c0 = kthId != IdLimits<int>::max() ? -kthKey - e : -CUDART_INF_F;
+            const int fid = w.q.ids[kFrac - 1];
+            const float c1 = fid != IdLimits<int>::max() ? -w.q.keys[kFrac - 1] - e : -CUDART_INF_F;
+            contrib[q] = c0;
+            contrib[nq + q] = -c1; // max-reduced: -min_r c1 (+inf if any shard cannot vouch for kFrac rows)
+        }
+    }
+}
+
+// sharded search: fold the all-reduced (max) contributions into the local threshold
+__global__ void tc_pooled_thr_kernel(int nq, const float* __restrict__ contrib, const float* __restrict__ eps, float* __restrict__ thr) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq)
+        return;
+    const float T = fmaxf(contrib[q], -contrib[nq + q]);
+    if (T > -CUDART_INF_F) {
+        const float t = nextafterf(T - eps[q], -CUDART_INF_F);
+        thr[q] = fmaxf(thr[q], t);
     }
 }
 
@@ -288,6 +318,8 @@ __global__ void tc_rerank_kernel(
         const float* __restrict__ Y,
         const int* __restrict__ perm, // stored (norm-sorted) position -> row id; null: identity
         const int* __restrict__ baseId,
+        const float* __restrict__ baseKey, // with thr: entries whose approximate score is <= thr[q] are skipped
+        const float* __restrict__ thr,     // (the threshold may have been raised after the list was written); or null
         float* __restrict__ outD,
         idx_t* __restrict__ outI) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,9 +334,12 @@ __global__ void tc_rerank_kernel(
     w.init(reinterpret_cast<float*>(base), reinterpret_cast<int*>(base + sizeof(float) * (KL + BUF)), KL, BUF, k);
     const float* qp = Q + (int64_t)q * d;
     const int* bi = baseId + (int64_t)q * LIST;
+    const float tq = thr ? thr[q] : -CUDART_INF_F;
     for (int e0 = 0; e0 < LIST; e0 += 32) {
         int id = bi[e0 + lane];
         bool valid = id != IdLimits<int>::max();
+        if (valid && thr)
+            valid = -baseKey[(int64_t)q * LIST + e0 + lane] > tq;
         if (valid && perm)
             id = perm[id];
         float acc = 0.f;
@@ -635,7 +670,8 @@ void runFlatTcSearch(
         MetricType metric,
         float* outD,
         idx_t* outI,
-        cudaStream_t stream) {
+        cudaStream_t stream,
+        const FlatTcShard* shard) {
     if (nqAll == 0)
         return;
     FB_THROW_IF_NOT(flatTcSupported(d, k, n));
@@ -643,6 +679,13 @@ void runFlatTcSearch(
     const SmemPlan sp = planSmem(KB);
     const int sms = res->numSMs(device);
     const int64_t T = ceil_div(n, kTileN);
+    // Sharded search: every rank runs the SAME number of rounds (one all-reduce per round), so the schedule
+    // is laid out over the largest shard's tile count and clamped to this shard's.  Thresholds are pooled
+    // across ranks after every round, i.e. a round over t local tiles is worth S*t tiles of evidence: the first
+    // round shrinks by S and the rounds grow faster (fewer launches for a 1/S-size shard).
+    const int nShards = shard ? shard->comm->size() : 1;
+    const int64_t Tsched = shard ? std::max<int64_t>(T, shard->maxTiles) : T;
+    const int kFrac = (k + nShards - 1) / nShards;
     const int LIST = std::max(128, next_pow2(2 * k));
     const int KL = std::max(64, next_pow2(k));
 
@@ -664,7 +707,9 @@ void runFlatTcSearch(
     // fixed 16 tiles would make small-k searches (k-means assignment: k = 1, millions of queries) pay 4096
     // candidates per query for nothing.
     static const int r0Env = getenv("FB200_TC_R0") ? atoi(getenv("FB200_TC_R0")) : 0;
-    const int r0Tiles = std::max(r0Env > 0 ? r0Env : std::max(1, (40 * k + kTileN - 1) / kTileN), (k + 127) / 128 * 2);
+    int r0Tiles = std::max(r0Env > 0 ? r0Env : std::max(1, (40 * k + kTileN - 1) / kTileN), (k + 127) / 128 * 2);
+    if (nShards > 1) // pooled evidence: nShards * r0Tiles tiles; a shard must still be able to vouch for kFrac rows
+        r0Tiles = std::max<int>((r0Tiles + nShards - 1) / nShards, std::max(2, (2 * kFrac + kTileN - 1) / kTileN));
     // queries per pass: bounds the candidate arena, whose largest user is the all-pass round 0
     // (512 KB per query pair and tile) -- 16384 queries at k = 100, up to 131072 for small k
     const int64_t kQBatch = std::min<int64_t>(131072, std::max<int64_t>(16384, (int64_t)kPairM * 1024 / r0Tiles));
@@ -706,16 +751,17 @@ void runFlatTcSearch(
         std::vector<Round> rounds;
         {
             int64_t seen = 0;
-            while (seen < T) {
+            while (seen < Tsched) {
                 // schedule knobs (tuning only): first-round tiles, early / late growth factors
                 static const double gEarly = getenv("FB200_TC_G_EARLY") ? atof(getenv("FB200_TC_G_EARLY")) : 4.0;
                 static const double gLate = getenv("FB200_TC_G_LATE") ? atof(getenv("FB200_TC_G_LATE")) : 4.0;
                 static const int64_t lateFrom = getenv("FB200_TC_LATE_FROM") ? atol(getenv("FB200_TC_LATE_FROM")) : 8192;
-                const double g = seen >= lateFrom ? gLate : gEarly;
-                int64_t end = seen == 0 ? std::min<int64_t>(T, r0Tiles)
-                                        : std::min<int64_t>(T, (int64_t)(seen * g));
-                if (T - end < end / 4)
-                    end = T; // do not leave a sliver for an extra round
+                static const double gShard = getenv("FB200_TC_G_SHARD") ? atof(getenv("FB200_TC_G_SHARD")) : 8.0;
+                const double g = nShards > 1 ? std::max(gEarly, std::min(gShard, 2.0 * nShards)) : (seen >= lateFrom ? gLate : gEarly);
+                int64_t end = seen == 0 ? std::min<int64_t>(Tsched, r0Tiles)
+                                        : std::min<int64_t>(Tsched, (int64_t)(seen * g));
+                if (Tsched - end < end / 4)
+                    end = Tsched; // do not leave a sliver for an extra round
                 int64_t tiles = end - seen;
                 // choose the slice count minimising (waves x tiles per slice)
                 int bestS = 1;
@@ -758,14 +804,17 @@ void runFlatTcSearch(
         const size_t selSmem = SmemTopK<int>::bytes(LIST, kSelectBuf) * selWarps;
         CUDA_VERIFY(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)selSmem));
 
+        GpuMemoryReservation contrib;
+        if (shard)
+            contrib = res->temp(device, sizeof(float) * 2 * nq);
         for (auto& r : rounds) {
             TcParams p{};
             p.slices = r.slices;
             p.qPairs = (int)qPairs;
             p.numUnits = (int)(qPairs * r.slices);
             CUtensorMap mapQ = makeTileMap(q16.as<__half>(), qPairs * kPairM, dpad, kTileM);
-            p.tileBegin = r.begin;
-            p.tileEnd = r.end;
+            p.tileBegin = (int)std::min<int64_t>(r.begin, T); // schedule laid out over the largest shard: clamp to ours
+            p.tileEnd = (int)std::min<int64_t>(r.end, T);
             p.tilesPerSlice = r.tilesPerSlice;
             p.permA = A;
             p.permB = B;
@@ -782,7 +831,11 @@ void runFlatTcSearch(
             p.dump = nullptr;
             p.dumpLd = 0;
             p.nq = (int)nq;
-            launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+            if (p.tileBegin < p.tileEnd) {
+                launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+            } else { // this shard has no tiles in this round of the common schedule: no candidates
+                CUDA_VERIFY(cudaMemsetAsync(counts.data, 0, (size_t)p.numUnits * tcSegsPerUnit(parts) * sizeof(int), stream));
+            }
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
                     k,
@@ -796,8 +849,18 @@ void runFlatTcSearch(
                     baseKey.as<float>(),
                     baseId.as<int>(),
                     thr.as<float>(),
-                    flags.as<int>());
+                    flags.as<int>(),
+                    shard ? contrib.as<float>() : nullptr,
+                    kFrac);
             CUDA_CHECK_LAST();
+            if (shard) {
+                // ONE small all-reduce per round (2 floats per query): every shard then filters against a
+                // threshold certified by the pooled evidence of all shards
+                shard->comm->allReduceMax(contrib.as<float>(), (size_t)2 * nq, stream);
+                tc_pooled_thr_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(
+                        (int)nq, contrib.as<float>(), eps.as<float>(), thr.as<float>());
+                CUDA_CHECK_LAST();
+            }
         }
 
         // ---- exact re-rank
@@ -811,7 +874,8 @@ void runFlatTcSearch(
             auto launchRr = [&](auto kern) {
                 CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rrSmem));
                 kern<<<(unsigned)ceil_div(nq, rrWarps), rrWarps * 32, rrSmem, stream>>>(
-                        (int)nq, d, k, LIST, KL, Qb, Y, perm, baseId.as<int>(), oD, oI);
+                        (int)nq, d, k, LIST, KL, Qb, Y, perm, baseId.as<int>(), baseKey.as<float>(),
+                        shard ? thr.as<float>() : nullptr, oD, oI);
             };
             if (metric == METRIC_L2)
                 launchRr(tc_rerank_kernel<true>);

@@ -1,6 +1,8 @@
 // faiss_b200 -- host-side index objects.  See index.h for the reference map.
 #include "index.h"
 
+#include "comm.h"
+
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -406,6 +408,26 @@ void GpuIndexFlat::searchImpl_(idx_t n, const float* xDev, int k, float* dDev, i
                 resources_.get(), config_.device, xDev, n, vecs_.data(), this->ntotal, d, k, metric_type, 0, dDev, iDev,
                 stream);
     }
+}
+
+bool GpuIndexFlat::shardPoolingEligible(int k, idx_t n) const {
+    return flatConfig_.useTensorCores && this->ntotal > 0 && flatTcSupported(d, k, this->ntotal) && n >= 16;
+}
+
+void GpuIndexFlat::searchShardDevice(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev, const FlatTcShard* flatShard) const {
+    if (!flatShard) {
+        searchImpl_(n, xDev, k, dDev, iDev);
+        return;
+    }
+    FB_THROW_IF_NOT_MSG(shardPoolingEligible(k, n), "pooled sharded search requested on a shard that cannot take the tensor-core path");
+    auto stream = stream_();
+    prepareTensorCoreData_();
+    runFlatTcSearch(
+            resources_.get(), config_.device, xDev, n, vecs_.data(), y16_.data(), bias_.data(),
+            metric_type == METRIC_L2 ? perm_.data() : nullptr, tileMaxBias_.data(), yScale_, yMaxNorm_, this->ntotal, d,
+            dpad_, k, metric_type, dDev, iDev, stream, flatShard);
+    lastSearchUsedTensorCores = 1;
+    lastSearchFallbackQueries = lastFlatTcFallbacks();
 }
 
 void GpuIndexFlat::reconstruct(idx_t key, float* out) const {
@@ -1481,6 +1503,11 @@ void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx
     FB_THROW_IF_NOT(k > 0);
     const idx_t nshard = count();
     FB_THROW_IF_NOT_MSG(nshard > 0, "no shards");
+    lastSearchPath = 0;
+    if (ncclFastPath_(n, x, k, distances, labels)) {
+        lastSearchPath = 1;
+        return;
+    }
     std::vector<idx_t> translations(nshard, 0);
     if (successive_ids) {
         translations[0] = 0;
@@ -1504,6 +1531,193 @@ void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx
         }
     });
     merge_knn_results_host(n, k, (int)nshard, metric_type, ad, al, distances, labels);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// DistributedIndexShards
+// ------------------------------------------------------------------------------------------
+DistributedIndexShards::DistributedIndexShards(std::shared_ptr<GpuResources> resources, GpuIndex* local, bool successive)
+        : Index(local->d, local->metric_type), successive_ids(successive), resources_(std::move(resources)), local_(local) {
+    FB_THROW_IF_NOT_MSG(local_ != nullptr, "null local shard");
+    comm_ = resources_->getCommunicator(local_->getDevice());
+    FB_THROW_IF_NOT_MSG(
+            comm_ != nullptr,
+            "no NCCL communicator for the shard's device: call ncclInitRank / ncclInitAll on the resources first");
+    syncWithSubIndexes();
+}
+
+DistributedIndexShards::~DistributedIndexShards() {
+    if (dOffsets_) {
+        DeviceScope scope(local_->getDevice());
+        cudaFree(dOffsets_);
+    }
+    if (own_local)
+        delete local_;
+}
+
+int DistributedIndexShards::rank() const {
+    return comm_->rank();
+}
+int DistributedIndexShards::worldSize() const {
+    return comm_->size();
+}
+
+void DistributedIndexShards::syncWithSubIndexes() {
+    const int device = local_->getDevice();
+    DeviceScope scope(device);
+    cudaStream_t stream = resources_->getDefaultStream(device);
+    // one tiny collective: every rank's (ntotal, "can take the pooled tensor-core path") pair
+    const bool flatTc = dynamic_cast<GpuIndexFlat*>(local_) != nullptr && local_->shardPoolingEligible(1, 16);
+    std::vector<int64_t> v = comm_->allGatherHostI64(local_->ntotal * 2 + (flatTc ? 1 : 0), stream);
+    const int S = comm_->size();
+    sizes_.assign(S, 0);
+    allFlatTc_ = true;
+    this->ntotal = 0;
+    maxTiles_ = 0;
+    std::vector<idx_t> offs(S, 0);
+    idx_t run = 0;
+    for (int r = 0; r < S; r++) {
+        sizes_[r] = v[r] >> 1;
+        allFlatTc_ = allFlatTc_ && (v[r] & 1);
+        if (r == comm_->rank())
+            idOffset_ = successive_ids ? run : 0;
+        offs[r] = successive_ids ? run : 0;
+        run += sizes_[r];
+        maxTiles_ = std::max<int64_t>(maxTiles_, ceil_div(sizes_[r], (idx_t)256));
+    }
+    this->ntotal = run;
+    this->is_trained = local_->is_trained;
+    if (!dOffsets_)
+        CUDA_VERIFY(cudaMalloc(&dOffsets_, sizeof(idx_t) * S));
+    CUDA_VERIFY(cudaMemcpyAsync(dOffsets_, offs.data(), sizeof(idx_t) * S, cudaMemcpyHostToDevice, stream));
+    CUDA_VERIFY(cudaStreamSynchronize(stream));
+}
+
+void DistributedIndexShards::train(idx_t n, const float* x) {
+    local_->train(n, x);
+    this->is_trained = local_->is_trained;
+}
+
+void DistributedIndexShards::add(idx_t n, const float* x) {
+    FB_THROW_IF_NOT_MSG(
+            !successive_ids || local_->ntotal == 0,
+            "when adding to IndexShards with successive_ids, only add() in a single pass is supported");
+    local_->add(n, x);
+    syncWithSubIndexes();
+}
+
+void DistributedIndexShards::add_with_ids(idx_t n, const float* x, const idx_t* xids) {
+    FB_THROW_IF_NOT_MSG(!(successive_ids && xids), "It makes no sense to pass in ids and request them to be shifted");
+    local_->add_with_ids(n, x, xids);
+    syncWithSubIndexes();
+}
+
+void DistributedIndexShards::reset() {
+    local_->reset();
+    syncWithSubIndexes();
+}
+
+void DistributedIndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const {
+    searchCollective(n, x, k, distances, labels, true);
+}
+
+void DistributedIndexShards::searchCollective(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, bool wantResult) const {
+    FB_THROW_IF_NOT(k > 0);
+    validateKSelect(k);
+    if (n == 0)
+        return;
+    const int device = local_->getDevice();
+    DeviceScope scope(device);
+    GpuResources* res = resources_.get();
+    cudaStream_t stream = res->getDefaultStream(device);
+    const int S = comm_->size();
+    // the pooled-threshold protocol only if EVERY rank takes the tensor-core Flat path for this (k, n):
+    // decided from data every rank holds identically (gathered sizes and flags), never from local state
+    bool pooled = allFlatTc_ && n >= 16;
+    for (int r = 0; r < S && pooled; r++)
+        pooled = flatTcSupported(d, (int)k, sizes_[r]);
+    FlatTcShard ctx{comm_.get(), maxTiles_};
+    // query pages bound the gathered staging ([S][page][k] x 12 bytes)
+    const idx_t maxQ = std::max<idx_t>(1, std::min<idx_t>(idx_t(1) << 18, (idx_t)((size_t(768) << 20) / ((size_t)S * k * 12))));
+    for (idx_t i0 = 0; i0 < n; i0 += maxQ) {
+        const idx_t nb = std::min(maxQ, n - i0);
+        DeviceView<float> xv(res, device, x + (size_t)i0 * d, (size_t)nb * d, stream);
+        auto locD = res->temp(device, sizeof(float) * nb * k);
+        auto locI = res->temp(device, sizeof(idx_t) * nb * k);
+        local_->searchShardDevice(nb, xv.ptr, (int)k, locD.as<float>(), locI.as<idx_t>(), pooled ? &ctx : nullptr);
+        auto allD = res->temp(device, sizeof(float) * (size_t)S * nb * k);
+        auto allI = res->temp(device, sizeof(idx_t) * (size_t)S * nb * k);
+        // ONE exchange: the per-shard [nb,k] distance and label blocks, fused into a single NCCL launch
+        KernelTiming::begin("shards_exchange", stream);
+        comm_->allGatherPair(locD.as<float>(), allD.as<float>(), (size_t)nb * k, locI.as<idx_t>(), allI.as<idx_t>(), (size_t)nb * k, stream);
+        KernelTiming::end("shards_exchange", stream);
+        if (wantResult) {
+            DeviceOut<float> dv(res, device, distances + (size_t)i0 * k, (size_t)nb * k);
+            DeviceOut<idx_t> lv(res, device, labels + (size_t)i0 * k, (size_t)nb * k);
+            KernelTiming::begin("shards_merge", stream);
+            runMergeTopKListMajor(allD.as<float>(), allI.as<idx_t>(), nb, S, (int)k, dOffsets_, (int)k, metric_type, dv.ptr, lv.ptr, stream);
+            KernelTiming::end("shards_merge", stream);
+            dv.finish(stream);
+            lv.finish(stream);
+            if (dv.staged || lv.staged || xv.hold.data)
+                CUDA_VERIFY(cudaStreamSynchronize(stream));
+        } else {
+            CUDA_VERIFY(cudaStreamSynchronize(stream)); // staging buffers die here
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// IndexShards: in-process NCCL fast path
+// ------------------------------------------------------------------------------------------
+bool IndexShards::ncclFastPath_(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const {
+    const int S = count();
+    if (S < 2 || k > kMaxK)
+        return false;
+    std::vector<GpuIndex*> gs(S);
+    std::vector<int> seen;
+    for (int i = 0; i < S; i++) {
+        gs[i] = dynamic_cast<GpuIndex*>(shards_[i]);
+        if (!gs[i])
+            return false;
+        const int dev = gs[i]->getDevice();
+        if (std::find(seen.begin(), seen.end(), dev) != seen.end())
+            return false; // two shards on one device: the clique has one rank per device
+        seen.push_back(dev);
+        auto c = gs[i]->getResources()->getCommunicator(dev);
+        if (!c || c->size() != S || c->rank() != i)
+            return false; // shard order must be rank order (the id translation follows it)
+    }
+    // (re)build the per-device wrappers when the shard set or the sizes changed; construction and
+    // syncWithSubIndexes are collectives, so they run on one thread per device like the search
+    bool stale = (int)dist_.size() != S;
+    for (int i = 0; i < S && !stale; i++)
+        stale = dist_[i]->local() != gs[i] || dist_[i]->successive_ids != successive_ids || dist_[i]->shardSize(i) != gs[i]->ntotal;
+    std::vector<std::string> errors(S);
+    auto runAll = [&](auto body) {
+        std::vector<std::thread> th;
+        for (int i = 0; i < S; i++)
+            th.emplace_back([&, i] {
+                try {
+                    body(i);
+                } catch (const std::exception& e) {
+                    errors[i] = e.what();
+                }
+            });
+        for (auto& t : th)
+            t.join();
+        for (int i = 0; i < S; i++)
+            if (!errors[i].empty())
+                FB_THROW_FMT("Exception thrown from index %d: %s", i, errors[i].c_str());
+    };
+    if (stale) {
+        dist_.clear();
+        dist_.resize(S);
+        runAll([&](int i) { dist_[i].reset(new DistributedIndexShards(gs[i]->getResources(), gs[i], successive_ids)); });
+    }
+    runAll([&](int i) { dist_[i]->searchCollective(n, x, k, distances, labels, i == 0); });
+    return true;
 }
 
 } // namespace fb200

@@ -157,6 +157,22 @@ class GpuIndex : public Index {
     virtual void addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) = 0;
     virtual void searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const = 0;
 
+   public:
+    // Shard-local half of a sharded search (device pointers, ids local to this shard).  `flatShard` is
+    // non-null only when EVERY rank of the communicator runs the tensor-core Flat path: the ranks then pool
+    // their thresholds after every round, and a shard may return fewer than k entries (-1 padded) -- those it
+    // can prove are not in the global top-k.  All ranks must make the call with identical queries and k.
+    virtual void searchShardDevice(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev, const FlatTcShard* flatShard) const {
+        (void)flatShard;
+        searchImpl_(n, xDev, k, dDev, iDev);
+    }
+    // would this index take the tensor-core Flat path for (its current size, k)?  (sharded search: the
+    // pooled-threshold protocol is used only if this holds on every rank)
+    virtual bool shardPoolingEligible(int /*k*/, idx_t /*n*/) const {
+        return false;
+    }
+
+   protected:
     cudaStream_t stream_() const {
         return resources_->getDefaultStream(config_.device);
     }
@@ -205,6 +221,8 @@ class GpuIndexFlat : public GpuIndex {
     void searchDevice(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const {
         searchImpl_(n, xDev, k, dDev, iDev);
     }
+    void searchShardDevice(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev, const FlatTcShard* flatShard) const override;
+    bool shardPoolingEligible(int k, idx_t n) const override;
     const float* vectorsDevice() const {
         return vecs_.data();
     }
@@ -532,6 +550,8 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
 // ------------------------------------------------------------------------------------------
 // IndexShards
 // ------------------------------------------------------------------------------------------
+class DistributedIndexShards;
+
 class IndexShards : public Index {
    public:
     explicit IndexShards(int d, bool threaded = false, bool successive_ids = true);
@@ -554,11 +574,70 @@ class IndexShards : public Index {
     void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const override;
     void reset() override;
     void syncWithSubIndexes();
+    // which path the last search took: 0 = thread-per-shard + host merge (the reference's), 1 = NCCL fast path
+    mutable int lastSearchPath = 0;
 
    private:
     template <typename F>
     void runOnIndex(F f) const;
+    // fast path: every shard is a GpuIndex on its own device and the shards' resources hold one NCCL clique
+    // over exactly those devices -> per-device threads + ncclAllGather + device merge (no host merge)
+    bool ncclFastPath_(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const;
     std::vector<Index*> shards_;
+    mutable std::vector<std::unique_ptr<DistributedIndexShards>> dist_; // one per device, built on first use
+};
+
+// ------------------------------------------------------------------------------------------
+// IndexShards across NCCL ranks: one shard (a GpuIndex) per rank of the resources' communicator for the
+// shard's device.  Same semantics as faiss::IndexShards::search (faiss/IndexShards.cpp:197-264): every query
+// goes to every shard, ids are translated by the number of vectors in lower-ranked shards when successive_ids,
+// results are merged with the (distance, id) rule of merge_knn_results (faiss/utils/Heap.cpp:166-238) --
+// but the exchange is ONE grouped ncclAllGather of the per-shard [n,k] blocks over NVLink and the merge a
+// device kernel reading the gathered layout in place.  With Flat shards on the tensor-core path the ranks
+// also pool their k-th-score thresholds after every round (one small all-reduce), so per-query work
+// (candidate selection, exact re-rank) shrinks with the number of shards instead of being replicated.
+// Used by: one process per GPU (every process holds one instance; search() is a collective call), and by
+// IndexShards' in-process fast path (one instance per device, driven by one thread per device).
+// ------------------------------------------------------------------------------------------
+class DistributedIndexShards : public Index {
+   public:
+    DistributedIndexShards(std::shared_ptr<GpuResources> resources, GpuIndex* local, bool successive_ids = true);
+    ~DistributedIndexShards() override;
+    bool own_local = false;
+    bool successive_ids;
+
+    int rank() const;
+    int worldSize() const;
+    idx_t idOffset() const {
+        return idOffset_;
+    }
+    GpuIndex* local() {
+        return local_;
+    }
+    // collective: re-reads every shard's ntotal (call after adds)
+    void syncWithSubIndexes();
+    void train(idx_t n, const float* x) override;           // local shard trains on x
+    void add(idx_t n, const float* x) override;              // adds x to the LOCAL shard, then syncWithSubIndexes()
+    void add_with_ids(idx_t n, const float* x, const idx_t* xids) override;
+    void reset() override;
+    // collective; x / distances / labels host or device, identical x on every rank
+    void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const override;
+    // the collective itself; a rank that does not need the merged result (in-process fast path: only one
+    // caller-visible output) skips the merge
+    void searchCollective(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, bool wantResult) const;
+    idx_t shardSize(int r) const {
+        return sizes_[r];
+    }
+
+   private:
+    std::shared_ptr<GpuResources> resources_;
+    GpuIndex* local_;
+    std::shared_ptr<Communicator> comm_;
+    std::vector<idx_t> sizes_;
+    bool allFlatTc_ = false; // every rank's shard is a tensor-core-capable GpuIndexFlat
+    idx_t idOffset_ = 0;
+    int64_t maxTiles_ = 0;
+    idx_t* dOffsets_ = nullptr; // device [world]
 };
 
 // host merge with the reference semantics (faiss/utils/Heap.cpp:166-238)

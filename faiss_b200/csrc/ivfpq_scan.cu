@@ -88,8 +88,7 @@ __device__ __forceinline__ unsigned prmt(unsigned a, unsigned b) {
     return d;
 }
 
-// ld.shared with the table's shared-window base folded into the instruction's immediate (LDS [R + imm]):
-// the PRMT result is then the complete address and a lookup is PRMT + LDS + FADD.
+// ld.shared with a compile-time byte offset: LDS R, [Raddr + imm]
 template <int IMM>
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
@@ -101,12 +100,6 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float v0, float v1) {
     asm("{\n.reg .b64 ra, rv, rd;\nmov.b64 ra, {%0,%1};\nmov.b64 rv, {%2,%3};\nadd.rn.f32x2 rd, ra, rv;\nmov.b64 {%0,%1}, rd;\n}"
         : "+f"(a0), "+f"(a1)
         : "f"(v0), "f"(v1));
-}
-
-__global__ void smem_base_probe_kernel(unsigned* out) {
-    extern __shared__ __align__(16) unsigned char probe_raw[];
-    if (threadIdx.x == 0)
-        *out = (unsigned)__cvta_generic_to_shared(probe_raw);
 }
 
 // One CTA = one query x one chunk of its probes, kWarps warps.
@@ -122,10 +115,12 @@ __global__ void smem_base_probe_kernel(unsigned* out) {
 //     of a list is amortised over two.  IP (and any list-independent table) needs no barrier at all.
 //   * inner loop per lookup: PRMT (code byte -> row, packed per-lane slot byte -> column) + LDS + FADD.
 // Keys: L2 -> sum of LUT entries (+ ||x - c||^2 with precomputed tables); IP -> -(q.centroid) - sum.
-// SBASE: shared-window address of the dynamic shared memory when it is known on the host (probed once per
-// device), folded into the LDS immediate; -1 = generic (one extra IADD per lookup).  FADD2: packed adds.
-template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int SBASE, bool FADD2>
-__global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_interleaved_kernel(
+// kU: groups of 32 vectors per work unit (kU * 32 * M bytes of codes in flight per warp); kMinCtas: CTAs per
+// SM the register budget is set for; ROLL: rolling prefetch of the next unit (L2 pairs); SBASE: shared-window address of the dynamic shared
+// memory (0x400 on sm_100: the first KB of the window is reserved), folded into the LDS immediate so that the
+// PRMT result IS the address; -1 = unknown (one extra IADD per lookup).
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int kU, int kMinCtas, bool ROLL, int SBASE>
+__global__ void __launch_bounds__(kWarps * 32, kMinCtas) ivfpq_scan_interleaved_kernel(
         const float* __restrict__ Q,
         int d,
         const idx_t* __restrict__ probes,
@@ -147,7 +142,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
     static_assert((kWarps & (kWarps - 1)) == 0, "kWarps must be a power of two");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreads = kWarps * 32;
-    constexpr int kU = M == 32 ? 4 : 8;      // groups per work unit: 4 KB of codes in flight per warp
     constexpr int H = M / 16;                // 16-byte words per lane and group
     constexpr int kEntriesPerThread = 256 * M / kThreads;
     static_assert(256 * M % kThreads == 0, "LUT entries must divide evenly among the threads");
@@ -166,11 +160,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
     top.init(listMem, ctl, LIST, k, kWarps);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(lut);
     if (SBASE >= 0 && sbase != (unsigned)SBASE)
-        __trap(); // the host probed a different base: refuse to read the wrong addresses
-    // per-lane column bytes: byte b of P0 = ((lane ^ b) << 2); word w of a vector uses P0 ^ (w << 4 in every byte)
+        __trap(); // compiled for another shared-window base: refuse to read the wrong addresses
+    // per-lane column byte of lookup j: X_j = ((lane ^ j) << 2) | (table << 7).  Three of them travel in one
+    // register (byte 3 stays zero and supplies the address's two high bytes), derived per triple with ONE
+    // LOP3 from Pbase = X_0 replicated: P_i = Pbase ^ {12i << 2, (12i + 4) ..} -- constants.
     const unsigned t4 = (unsigned)lane << 2;
-    const unsigned P0 = t4 | ((t4 ^ 4u) << 8) | ((t4 ^ 8u) << 16) | ((t4 ^ 12u) << 24);
-
     // direct LUT entry e = c*M + m from a vector r[d] in shared memory:
     //   L2: ||r|m - y||^2 (r = query - list centroid);  IP / PRECOMP term 3: <r|m, y> (r = query)
     auto entry = [&](const float* r, int e, bool l2form) {
@@ -215,60 +209,72 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
             lut[c * 64 + buf * 32 + s + m] = val;
     };
 
-    // one work unit: kU groups of 32 vectors of one list, looked up in table BUF
-    auto scanUnit = [&](auto bufTag, const uint8_t* codes, int ngroups, int g0, int len, int64_t ls, float add) {
-        constexpr int BUF = decltype(bufTag)::value;
+    // 32 vectors (one group, this lane's vector): sum of its M table entries in table `buf` (0 / 1: a runtime
+    // value folded into the column bytes, so there is ONE copy of the lookup code in the instruction cache)
+    auto groupSum = [&](const uint4 (&c)[H], unsigned Pbase) {
+        float a0 = 0.f, a1 = 0.f;
+        unsigned P = 0;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            const unsigned word = j / 4 % 4 == 0 ? c[j / 16].x : j / 4 % 4 == 1 ? c[j / 16].y : j / 4 % 4 == 2 ? c[j / 16].z : c[j / 16].w;
+            if (j % 3 == 0) { // column bytes of lookups j, j+1, j+2
+                const unsigned C = ((unsigned)(j) << 2) | (((unsigned)(j + 1) << 2) << 8) | (((unsigned)(j + 2) << 2) << 16);
+                P = Pbase ^ (C & 0x007c7c7cu);
+            }
+            // R = (code byte << 8) | column byte; bytes 2, 3 = byte 3 of P = 0
+            unsigned R;
+            switch ((j % 4) * 4 + j % 3) {
+                case 0: R = prmt<0x7704>(word, P); break;
+                case 1: R = prmt<0x7705>(word, P); break;
+                case 2: R = prmt<0x7706>(word, P); break;
+                case 4: R = prmt<0x7714>(word, P); break;
+                case 5: R = prmt<0x7715>(word, P); break;
+                case 6: R = prmt<0x7716>(word, P); break;
+                case 8: R = prmt<0x7724>(word, P); break;
+                case 9: R = prmt<0x7725>(word, P); break;
+                case 10: R = prmt<0x7726>(word, P); break;
+                case 12: R = prmt<0x7734>(word, P); break;
+                case 13: R = prmt<0x7735>(word, P); break;
+                default: R = prmt<0x7736>(word, P); break;
+            }
+            float v;
+            if (SBASE >= 0)
+                v = lds_f32<(SBASE >= 0 ? SBASE : 0)>(R);
+            else
+                v = lds_f32<0>(R + sbase);
+            if (j < 2) { // start the two chains without adding to zero
+                if (j == 0)
+                    a0 = v;
+                else
+                    a1 = v;
+            } else if (j & 1) {
+                a1 += v;
+            } else {
+                a0 += v;
+            }
+        }
+        return a0 + a1;
+    };
+    auto loadGroup = [&](const uint8_t* codes, int g, uint4 (&dst)[H]) {
+        const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
+#pragma unroll
+        for (int h = 0; h < H; h++)
+            dst[h] = __ldg(gp + h * 32);
+    };
+
+    // one work unit: kU groups of 32 vectors of one list, looked up in table `buf`
+    auto scanUnit = [&](int buf, const uint8_t* codes, int ngroups, int g0, int len, int64_t ls, float add) {
         uint4 cur[kU][H];
 #pragma unroll
-        for (int u = 0; u < kU; u++) {
-            const int g = min(g0 + u, ngroups - 1); // clamped: tail groups re-read the last one (masked below)
-            const uint4* gp = reinterpret_cast<const uint4*>(codes + (int64_t)g * 32 * M) + lane;
-#pragma unroll
-            for (int h = 0; h < H; h++)
-                cur[u][h] = __ldg(gp + h * 32);
-        }
+        for (int u = 0; u < kU; u++)
+            loadGroup(codes, min(g0 + u, ngroups - 1), cur[u]); // clamped: tail groups re-read the last one (masked below)
         top.refresh();
+        const unsigned Pbase = (t4 | ((unsigned)buf << 7)) * 0x010101u;
 #pragma unroll
         for (int u = 0; u < kU; u++) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int h = 0; h < H; h++) {
-                const unsigned wds[4] = {cur[u][h].x, cur[u][h].y, cur[u][h].z, cur[u][h].w};
-#pragma unroll
-                for (int wi = 0; wi < 4; wi++) {
-                    const unsigned P = P0 ^ ((unsigned)(h * 4 + wi) * 0x10101010u);
-                    // R = (code byte << 8) | column byte ; bytes 2, 3 = sign of a column byte (< 128) = 0
-                    unsigned R0 = prmt<0xCC04>(wds[wi], P);
-                    unsigned R1 = prmt<0xCC15>(wds[wi], P);
-                    unsigned R2 = prmt<0xCC26>(wds[wi], P);
-                    unsigned R3 = prmt<0xCC37>(wds[wi], P);
-                    constexpr int IMM = (SBASE >= 0 ? SBASE : 0) + BUF * 128;
-                    if (SBASE < 0) {
-                        R0 += sbase;
-                        R1 += sbase;
-                        R2 += sbase;
-                        R3 += sbase;
-                    }
-                    const float v0 = lds_f32<IMM>(R0), v1 = lds_f32<IMM>(R1), v2 = lds_f32<IMM>(R2), v3 = lds_f32<IMM>(R3);
-                    if (h == 0 && wi == 0) { // first word: start the two chains without adding to zero
-                        a0 = v0;
-                        a1 = v1;
-                    } else if (FADD2) {
-                        add2(a0, a1, v0, v1);
-                    } else {
-                        a0 += v0;
-                        a1 += v1;
-                    }
-                    if (FADD2) {
-                        add2(a0, a1, v2, v3);
-                    } else {
-                        a0 += v2;
-                        a1 += v3;
-                    }
-                }
-            }
+            const float sum = groupSum(cur[u], Pbase);
             const int v = (g0 + u) * 32 + lane;
-            const float key = (IS_L2 && !PRECOMP) ? a0 + a1 : (a0 + a1) + add;
+            const float key = (IS_L2 && !PRECOMP) ? sum : sum + add;
             top.add(g0 + u < ngroups && v < len, key, (IdT)(ls + v));
         }
     };
@@ -345,6 +351,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
 #pragma unroll
                     for (int i = 0; i < kEntriesPerThread; i++)
                         store(s, threadIdx.x + i * kThreads, v2[i] + t3[i]);
+                } else if (dsub == 4) {
+                    // every entry of this thread belongs to sub-quantiser m = tid % M (kThreads % M == 0): its slice
+                    // of the residual is read from shared memory ONCE per probe, not once per entry
+                    const float4 rv = *reinterpret_cast<const float4*>(rs + s * d + (threadIdx.x % M) * 4);
+#pragma unroll 8
+                    for (int e = threadIdx.x; e < 256 * M; e += kThreads) {
+                        const float4 cv = __ldg(reinterpret_cast<const float4*>(pqT + (size_t)e * 4));
+                        const float d0 = rv.x - cv.x, d1 = rv.y - cv.y, d2 = rv.z - cv.z, d3 = rv.w - cv.w;
+                        float acc = d0 * d0; // same association as entry(): fma chain from 0
+                        acc = fmaf(d1, d1, acc);
+                        acc = fmaf(d2, d2, acc);
+                        acc = fmaf(d3, d3, acc);
+                        store(s, e, acc);
+                    }
                 } else {
 #pragma unroll 8
                     for (int e = threadIdx.x; e < 256 * M; e += kThreads)
@@ -352,21 +372,67 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
                 }
             }
             __syncthreads();
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                if (len[s] == 0)
-                    continue;
-                const uint8_t* codes = arenaCodes + ls[s] * (int64_t)M;
-                const int ngroups = (len[s] + 31) >> 5;
-                const int units = (ngroups + kU - 1) / kU;
-                const float add = PRECOMP ? t1s[s] : 0.f;
-                for (int u = (warp - base) & (kWarps - 1); u < units; u += kWarps) {
-                    if (s == 0)
-                        scanUnit(std::integral_constant<int, 0>{}, codes, ngroups, u * kU, len[s], ls[s], add);
-                    else
-                        scanUnit(std::integral_constant<int, 1>{}, codes, ngroups, u * kU, len[s], ls[s], add);
+            if (!ROLL) {
+#pragma unroll 1
+                for (int s = 0; s < 2; s++) {
+                    if (len[s] == 0)
+                        continue;
+                    const uint8_t* codes = arenaCodes + ls[s] * (int64_t)M;
+                    const int ngroups = (len[s] + 31) >> 5;
+                    const int units = (ngroups + kU - 1) / kU;
+                    const float add = PRECOMP ? t1s[s] : 0.f;
+                    for (int u = (warp - base) & (kWarps - 1); u < units; u += kWarps)
+                        scanUnit(s, codes, ngroups, u * kU, len[s], ls[s], add);
+                    base += units;
                 }
-                base += units;
+            } else {
+                // Rolling prefetch: this warp's units of the pair form one stream; as soon as the lookups of a
+                // register slot are done the slot is refilled with the same slot of the warp's NEXT unit, so
+                // ~4 KB of code loads stay in flight per warp while it computes (no extra registers).
+                const int ng0 = (len[0] + 31) >> 5, ng1 = (len[1] + 31) >> 5;
+                const int un0 = (ng0 + kU - 1) / kU, un1 = (ng1 + kU - 1) / kU;
+                const uint8_t* c0 = arenaCodes + ls[0] * (int64_t)M;
+                const uint8_t* c1 = arenaCodes + ls[1] * (int64_t)M;
+                // stream position i = 0, 1, ...: global unit index gu = first + i * kWarps over [0, un0 + un1)
+                int gu = (warp - base) & (kWarps - 1);
+                const int total = un0 + un1;
+                uint4 cur[kU][H];
+                if (gu < total) {
+                    const bool in1 = gu >= un0;
+                    const uint8_t* cc = in1 ? c1 : c0;
+                    const int ng = in1 ? ng1 : ng0;
+                    const int g0 = (in1 ? gu - un0 : gu) * kU;
+#pragma unroll
+                    for (int u = 0; u < kU; u++)
+                        loadGroup(cc, min(g0 + u, ng - 1), cur[u]);
+                }
+                for (; gu < total; gu += kWarps) {
+                    const bool in1 = gu >= un0;
+                    const int ng = in1 ? ng1 : ng0;
+                    const int g0 = (in1 ? gu - un0 : gu) * kU;
+                    const int ln = in1 ? len[1] : len[0];
+                    const int64_t lsx = in1 ? ls[1] : ls[0];
+                    const float add = PRECOMP ? (in1 ? t1s[1] : t1s[0]) : 0.f;
+                    const unsigned Pbase = (t4 | (in1 ? 0x80u : 0u)) * 0x010101u;
+                    // next unit of this warp
+                    const int gn = gu + kWarps;
+                    const bool has = gn < total;
+                    const bool nin1 = gn >= un0;
+                    const uint8_t* nc = nin1 ? c1 : c0;
+                    const int nng = nin1 ? ng1 : ng0;
+                    const int ng0n = (nin1 ? gn - un0 : gn) * kU;
+                    top.refresh();
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const float sum = groupSum(cur[u], Pbase);
+                        if (has)
+                            loadGroup(nc, min(ng0n + u, nng - 1), cur[u]); // slot u is free again: refill it
+                        const int v = (g0 + u) * 32 + lane;
+                        const float key = (IS_L2 && !PRECOMP) ? sum : sum + add;
+                        top.add(g0 + u < ng && v < ln, key, (IdT)(lsx + v));
+                    }
+                }
+                base += total;
             }
         }
     } else {
@@ -383,7 +449,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32)) ivfpq_scan_
             const int units = (ngroups + kU - 1) / kU;
             const float add = -coarseDis[(int64_t)q * nprobe + p];
             for (int u = (warp - base) & (kWarps - 1); u < units; u += kWarps)
-                scanUnit(std::integral_constant<int, 0>{}, codes, ngroups, u * kU, len, ls, add);
+                scanUnit(0, codes, ngroups, u * kU, len, ls, add);
             base += units;
         }
     }
@@ -467,7 +533,7 @@ void runIvfPqListFromInterleaved(const uint8_t* listCodes, int64_t len, int M, u
     CUDA_CHECK_LAST();
 }
 
-template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int SBASE, bool FADD2>
+template <int M, bool IS_L2, bool PRECOMP, typename IdT, int kWarps, int kU, int kMinCtas, bool ROLL, int SBASE>
 static void launchScanV(
         dim3 grid,
         size_t smem,
@@ -489,7 +555,7 @@ static void launchScanV(
         int LIST,
         float* partD,
         idx_t* partI) {
-    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, PRECOMP, IdT, kWarps, SBASE, FADD2>;
+    auto kern = ivfpq_scan_interleaved_kernel<M, IS_L2, PRECOMP, IdT, kWarps, kU, kMinCtas, ROLL, SBASE>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("ivfpq_scan", stream);
     kern<<<grid, kWarps * 32, smem, stream>>>(
@@ -499,11 +565,25 @@ static void launchScanV(
     CUDA_CHECK_LAST();
 }
 
-constexpr int kScanWarps = 16; // warps per CTA (8 -> 16: 66 -> 60 ms on the N=100M workload)
+// launch shapes (FB200_PQ_CFG selects one for A/B runs; see profiles/ for the measurements behind the default)
+//   0: 16 warps, 4 KB of codes in flight per warp, 2 CTAs/SM (64 registers)
+//   1: 16 warps, 2 KB per warp, 3 CTAs/SM (42 registers)      2: 32 warps, 2 KB per warp, 2 CTAs/SM (32 registers)
+static int scanConfig() {
+    static const int cfg = getenv("FB200_PQ_CFG") ? atoi(getenv("FB200_PQ_CFG")) : 0;
+    return cfg;
+}
+static int scanWarps() {
+    return scanConfig() == 2 ? 32 : 16;
+}
 
-// shared-window address of dynamic shared memory for this device (probed once); -1 if it is not the
-// value the fast instantiation was compiled for
-constexpr int kExpectedSmemBase = 1024; // sm_100: the first KB of a CTA's shared window is reserved
+__global__ void smem_base_probe_kernel(unsigned* out) {
+    extern __shared__ __align__(16) unsigned char probe_raw[];
+    if (threadIdx.x == 0)
+        *out = (unsigned)__cvta_generic_to_shared(probe_raw);
+}
+
+// shared-window address of dynamic shared memory on this device (probed once)
+constexpr int kExpectedSmemBase = 1024;
 static int probedSmemBase(int device, cudaStream_t stream) {
     static int cache[64];
     static bool have[64] = {};
@@ -527,15 +607,23 @@ static int probedSmemBase(int device, cudaStream_t stream) {
 
 template <int M, bool IS_L2, bool PRECOMP, typename IdT, typename... Args>
 static void launchScan(int smemBase, Args... args) {
-    static const bool fadd2 = getenv("FB200_PQ_FADD2") ? atoi(getenv("FB200_PQ_FADD2")) != 0 : false;
-    static const bool generic = getenv("FB200_PQ_GENERIC_LDS") && atoi(getenv("FB200_PQ_GENERIC_LDS")) != 0;
-    if (smemBase == kExpectedSmemBase && !generic) {
-        if (fadd2)
-            launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, kExpectedSmemBase, true>(args...);
-        else
-            launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, kExpectedSmemBase, false>(args...);
-    } else {
-        launchScanV<M, IS_L2, PRECOMP, IdT, kScanWarps, -1, false>(args...);
+    constexpr int U = M == 32 ? 4 : 8; // groups per unit at 4 KB per warp
+    if (smemBase != kExpectedSmemBase) { // unknown shared-window base: generic addressing
+        launchScanV<M, IS_L2, PRECOMP, IdT, 16, U, 2, false, -1>(args...);
+        return;
+    }
+    switch (scanConfig()) {
+        case 1:
+            launchScanV<M, IS_L2, PRECOMP, IdT, 16, U / 2, 3, false, kExpectedSmemBase>(args...);
+            break;
+        case 2:
+            launchScanV<M, IS_L2, PRECOMP, IdT, 32, U / 2, 2, false, kExpectedSmemBase>(args...);
+            break;
+        case 3:
+            launchScanV<M, IS_L2, PRECOMP, IdT, 16, U, 2, true, kExpectedSmemBase>(args...);
+            break;
+        default:
+            launchScanV<M, IS_L2, PRECOMP, IdT, 16, U, 2, false, kExpectedSmemBase>(args...);
     }
 }
 
@@ -567,11 +655,12 @@ void runIvfPqScanInterleaved(
     FB_THROW_IF_NOT(ivfPqInterleavedSupported(M));
     const int LIST = std::max(64, next_pow2(k));
     const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
+    const int smemBase = probedSmemBase(device, stream);
+    const int kScanWarps = smemBase == kExpectedSmemBase ? scanWarps() : 16;
     const size_t listBytes = wide ? CtaTopK<long long>::bytes(LIST, kScanWarps) : CtaTopK<int>::bytes(LIST, kScanWarps);
     size_t smem = sizeof(float) * 256 * kLutSlots + round_up(sizeof(float) * 2 * d, 16) + 16 + listBytes;
     FB_THROW_IF_NOT_MSG(smem <= 220 * 1024, "LUT + top-k lists do not fit shared memory");
     const bool l2 = metric == METRIC_L2;
-    const int smemBase = probedSmemBase(device, stream);
     int probesPerCta = 1;
     const int chunks = ivfScanChunks(device, nq, nprobe, &probesPerCta);
     const int64_t maxQ = std::max<int64_t>(1, std::min<int64_t>(65535, (int64_t(1) << 30) / ((int64_t)chunks * k * 12)));

@@ -65,6 +65,21 @@ void runMergeTopK(
         idx_t* outI,
         cudaStream_t stream);
 
+// same merge over inputs laid out [nlists][rows][kin] (the layout an all-gather of per-shard results
+// produces: no permute copy between the collective and the merge)
+void runMergeTopKListMajor(
+        const float* inD,
+        const idx_t* inI,
+        int64_t rows,
+        int nlists,
+        int kin,
+        const idx_t* idOffsets,
+        int k,
+        MetricType metric,
+        float* outD,
+        idx_t* outI,
+        cudaStream_t stream);
+
 // residual x - c[assign] (NaN if assign = -1) ; role of runCalcResidual (VectorResidual.cu:26-176)
 void runCalcResidual(
         const float* x,
@@ -106,6 +121,15 @@ void runMaxOf(const float* x, int64_t count, float* out /*device, zeroed; x >= 0
 
 bool flatTcSupported(int d, int k, int64_t n);
 
+// Sharded search (one shard per NCCL rank): thresholds are pooled across the ranks after every round
+// (one all-reduce of 2 floats per query), so a 1/S-size shard filters as tightly as the whole database would
+// and keeps only its share of the global top-k; all ranks must call with the same queries and k.
+class Communicator;
+struct FlatTcShard {
+    const Communicator* comm; // this rank
+    int64_t maxTiles;         // max over ranks of ceil(n_r / 256): the common round schedule
+};
+
 // Full certified search: fp16 tcgen05 scoring + candidate emission + exact fp32 re-rank, with the
 // exact SIMT kernel as fallback for queries whose certificate fails.  See flat_tc.cu.
 void runFlatTcSearch(
@@ -127,7 +151,8 @@ void runFlatTcSearch(
         MetricType metric,
         float* outD,
         idx_t* outI,
-        cudaStream_t stream);
+        cudaStream_t stream,
+        const FlatTcShard* shard = nullptr);
 
 // number of queries the last runFlatTcSearch on this thread recomputed with the exact kernel
 int& lastFlatTcFallbacks();

@@ -1,6 +1,8 @@
 // faiss_b200 -- StandardGpuResources implementation.  See resources.h for the reference map.
 #include "resources.h"
 
+#include "comm.h"
+
 #include <algorithm>
 
 namespace fb200 {
@@ -397,8 +399,38 @@ struct TimedLaunch {
 std::mutex g_tmu;
 bool g_timing = false;
 std::vector<TimedLaunch> g_timed;
-cudaEvent_t g_pendingStart = nullptr;
+thread_local cudaEvent_t g_pendingStart = nullptr; // begin/end pair up per launching thread
 } // namespace
+
+void StandardGpuResources::ncclInitAll(const std::vector<int>& devices) {
+    for (int d : devices)
+        initializeForDevice(d);
+    auto comms = Communicator::initAll(devices);
+    std::lock_guard<std::recursive_mutex> g(mu_);
+    for (size_t i = 0; i < devices.size(); i++)
+        comms_[devices[i]] = comms[i];
+}
+
+void StandardGpuResources::ncclInitRank(int device, int nranks, int rank, const char* uniqueId128) {
+    initializeForDevice(device);
+    auto c = Communicator::initRank(device, nranks, rank, uniqueId128);
+    std::lock_guard<std::recursive_mutex> g(mu_);
+    comms_[device] = c;
+}
+
+void StandardGpuResources::setCommunicator(int device, std::shared_ptr<Communicator> comm) {
+    std::lock_guard<std::recursive_mutex> g(mu_);
+    if (comm)
+        comms_[device] = std::move(comm);
+    else
+        comms_.erase(device);
+}
+
+std::shared_ptr<Communicator> StandardGpuResources::getCommunicator(int device) {
+    std::lock_guard<std::recursive_mutex> g(mu_);
+    auto it = comms_.find(device);
+    return it == comms_.end() ? nullptr : it->second;
+}
 
 void KernelTiming::enable(bool on) {
     std::lock_guard<std::mutex> g(g_tmu);

@@ -40,6 +40,7 @@ struct AllocRequest { // faiss/gpu/GpuResources.h:107-139
 };
 
 class GpuResources;
+class Communicator; // comm.h: one NCCL rank bound to a device
 
 // RAII reservation (faiss/gpu/GpuResources.h:172-195)
 struct GpuMemoryReservation {
@@ -80,6 +81,11 @@ class GpuResources { // faiss/gpu/GpuResources.h:200-281
     virtual size_t getTempMemoryAvailable(int device) const = 0;
     virtual std::pair<void*, size_t> getPinnedMemory() = 0;
     virtual int numSMs(int device) = 0;
+    // the NCCL rank this resources object holds for `device` (null: the device is not part of a
+    // communicator) -- SURVEY 7 step 1: NCCL communicator ownership lives with the resources
+    virtual std::shared_ptr<Communicator> getCommunicator(int /*device*/) {
+        return nullptr;
+    }
 
     GpuMemoryReservation allocMemoryHandle(const AllocRequest& req) {
         return GpuMemoryReservation(this, req.device, req.stream, allocMemory(req), req.size);
@@ -169,6 +175,13 @@ class StandardGpuResources : public GpuResources { // faiss/gpu/StandardGpuResou
     std::pair<void*, size_t> getPinnedMemory() override;
     int numSMs(int device) override;
 
+    // NCCL: one communicator per device.  ncclInitAll = every listed device of THIS process in one clique
+    // (rank i = devices[i]); ncclInitRank = this process is rank `rank` of `nranks` (one process per GPU).
+    void ncclInitAll(const std::vector<int>& devices);
+    void ncclInitRank(int device, int nranks, int rank, const char* uniqueId128);
+    void setCommunicator(int device, std::shared_ptr<Communicator> comm);
+    std::shared_ptr<Communicator> getCommunicator(int device) override;
+
     // GpuResourcesProvider::getResources() equivalent: the object is its own provider.
     GpuResources* getResources() {
         return this;
@@ -198,6 +211,7 @@ class StandardGpuResources : public GpuResources { // faiss/gpu/StandardGpuResou
     size_t pinnedAlloc_ = 0;
     bool allNull_ = false;
     bool logAlloc_ = false;
+    std::unordered_map<int, std::shared_ptr<Communicator>> comms_;
 };
 
 // RAII device switch (faiss/gpu/utils/DeviceUtils.h DeviceScope)

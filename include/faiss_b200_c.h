@@ -150,6 +150,29 @@ FB200_API void faiss_IndexShards_set_own_indices(FaissIndexShards* index, int v)
 FB200_API int faiss_IndexShards_successive_ids(const FaissIndexShards* index);
 FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int v);
 
+/* ---- NCCL communicator ownership + IndexShards across ranks ----
+   The reference shards over the GPUs of a box with IndexShards (one worker thread per sub-index, host heap
+   merge: faiss/IndexShards.cpp:197-264, faiss/impl/ThreadedIndex-inl.h:119-194); ToGpuClonerMultiple builds it
+   (faiss/gpu/GpuCloner.cpp:418-436).  Here the resources object owns one NCCL communicator per device:
+     ncclInitAll  -- all listed devices of THIS process form one clique (rank i = devices[i]); an IndexShards
+                     whose shards are GpuIndexes on exactly those devices, in rank order, then searches with
+                     per-device threads + one ncclAllGather + a device merge instead of the host merge;
+     ncclInitRank -- this process is rank `rank` of `nranks` (one process per GPU); the 128-byte id comes from
+                     faiss_b200_nccl_unique_id on one rank and reaches the others through the launcher.
+   faiss_DistributedIndexShards = IndexShards with ONE shard per rank: faiss_Index_search on it is a
+   collective call (identical queries and k on every rank), results on every rank; add() adds to the local
+   shard.  b200_shards_search is the one-shot kernel-seam form. */
+FB200_API int faiss_b200_nccl_unique_id(char* out128);
+FB200_API int faiss_StandardGpuResources_ncclInitRank(FaissStandardGpuResources* res, int device, int nranks, int rank, const char* unique_id128);
+FB200_API int faiss_StandardGpuResources_ncclInitAll(FaissStandardGpuResources* res, int ndev, const int* devices);
+FB200_API int faiss_StandardGpuResources_ncclRank(FaissStandardGpuResources* res, int device, int* rank, int* nranks);
+/* path of the last faiss_Index_search on an IndexShards: 0 = thread per shard + host merge, 1 = NCCL fast path */
+FB200_API int faiss_IndexShards_lastSearchPath(const FaissIndexShards* index);
+FB200_API int faiss_DistributedIndexShards_new(FaissIndexShards** p_index, FaissStandardGpuResources* res, FaissGpuIndex* local_shard, int successive_ids);
+FB200_API int faiss_DistributedIndexShards_sync(FaissIndexShards* index); /* collective: re-read every shard's ntotal */
+FB200_API int faiss_DistributedIndexShards_info(const FaissIndexShards* index, int* rank, int* nranks, idx_t* id_offset);
+FB200_API int b200_shards_search(FaissStandardGpuResources* res, FaissGpuIndex* local_shard, int successive_ids, idx_t n, const float* x, idx_t k, float* distances, idx_t* labels);
+
 /* ---- Clustering (c_api/Clustering_c.h faiss_kmeans_clustering; faiss/Clustering.cpp:60-380) ----
    Lloyd k-means with the training set resident on the device; x host or device. */
 FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, float* centroids_out /* host [k*d] */, float* obj_out /* host [niter] or NULL */);

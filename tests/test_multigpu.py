@@ -1,0 +1,73 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the sharded paths behind the C ABI --
+IndexShards' in-process NCCL fast path and DistributedIndexShards (one process per GPU) -- must return
+exactly what an unsharded index returns.  Model: faiss/gpu/test/test_multi_gpu.py:23-43,
+tests/test_meta_index.py (IndexShards == reference index)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def test_index_shards_nccl_fast_path_equals_unsharded():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import faiss_b200 as fb
+
+    ndev = min(_ngpu(), 4)
+    res = fb.StandardGpuResources()
+    res.ncclInitAll(list(range(ndev)))
+    rs = np.random.RandomState(5)
+    N, d, nq, k = 200_000, 96, 300, 40
+    xb = np.floor(rs.rand(N, d) * 16).astype(np.float32)
+    xq = np.floor(rs.rand(nq, d) * 16).astype(np.float32)
+    shards = fb.IndexShards(d, threaded=True, successive_ids=True)
+    subs = [fb.GpuIndexFlatL2(res, d, device=i) for i in range(ndev)]
+    for s in subs:
+        shards.add_shard(s)
+    shards.add(xb)
+    assert shards.ntotal == N
+    D, I = shards.search(xq, k)
+    assert shards.lastSearchPath() == "nccl"
+    full = fb.GpuIndexFlatL2(res, d, device=0, use_tensor_cores=False)
+    full.add(xb)
+    uD, uI = full.search(xq, k)
+    assert np.array_equal(I, uI) and np.array_equal(D, uD)
+    # a shard set the clique does not cover (two shards on one device) falls back to the host merge, same answer
+    shards2 = fb.IndexShards(d, threaded=False, successive_ids=True)
+    a, b = fb.GpuIndexFlatL2(res, d, device=0), fb.GpuIndexFlatL2(res, d, device=0)
+    shards2.add_shard(a)
+    shards2.add_shard(b)
+    shards2.add(xb)
+    D2, I2 = shards2.search(xq, k)
+    assert shards2.lastSearchPath() == "host"
+    assert np.array_equal(I2, uI) and np.array_equal(D2, uD)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_index_shards_processes(world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "_dist_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    out = json.loads(line[len("RESULT "):])
+    assert out["world"] == world
+    for name in ("flat_float", "flat_int", "flat_ip_small", "ivfflat_idmod"):
+        assert out[name]["ids_equal"] and out[name]["distances_equal"], (name, out[name])
+    assert out["flat_float"]["tensor_cores"] == 1 and out["flat_float"]["device_queries_equal"]
