@@ -401,6 +401,108 @@ __global__ void tc_init_base_kernel(float* baseKey, int* baseId, int64_t count) 
     }
 }
 
+// k = 1 streaming mode: select + exact re-rank in one pass.  One warp per query: (1) the maximum approximate
+// score m over the query's candidate segments, (2) every candidate scoring >= m - 2 eps (typically one to three)
+// gets its canonical fp32 distance -- one lane per candidate, sequential FMA over the dimension exactly like
+// flat_exact.cu -- (3) the (distance, id) minimum is the answer.  A segment that overflowed flags the query for
+// the exact kernel.
+template <bool IS_L2>
+__global__ void tc_argmin_finish_kernel(
+        int nq,
+        int d,
+        int slices,
+        int parts,
+        const uint2* __restrict__ cand,
+        int cap,
+        const int* __restrict__ candCount,
+        const float* __restrict__ eps,
+        const float* __restrict__ Q,
+        const float* __restrict__ Y,
+        const int* __restrict__ perm,
+        float* __restrict__ outD,
+        idx_t* __restrict__ outI,
+        int* __restrict__ flags) {
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+    const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq)
+        return;
+    const int pair = q / kPairM, prow = q % kPairM;
+    const int qPairs = (nq + kPairM - 1) / kPairM;
+    const int nseg = slices * parts;
+    // pass 1: maximum approximate score
+    float m = -CUDART_INF_F;
+    int overflow = 0;
+    for (int si = 0; si < nseg; si++) {
+        const int s = si / parts, h = si - s * parts;
+        const long long seg = ((long long)(s * qPairs + pair) * kPairM + prow) * parts + h;
+        int c = candCount[seg];
+        if (c > cap) {
+            overflow = 1;
+            c = cap;
+        }
+        const uint2* sp = cand + seg * cap;
+        for (int e = lane; e < c; e += 32)
+            m = fmaxf(m, __uint_as_float(sp[e].x));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+    const float t = nextafterf(m - 2.f * eps[q], -CUDART_INF_F);
+    // pass 2: exact distances of the survivors, best (distance, id)
+    float bestD = CUDART_INF_F;
+    int bestI = IdLimits<int>::max();
+    const float* qp = Q + (int64_t)q * d;
+    for (int si = 0; si < nseg; si++) {
+        const int s = si / parts, h = si - s * parts;
+        const long long seg = ((long long)(s * qPairs + pair) * kPairM + prow) * parts + h;
+        const int c = min(candCount[seg], cap);
+        const uint2* sp = cand + seg * cap;
+        for (int e0 = 0; e0 < c; e0 += 32) {
+            const int e = e0 + lane;
+            const uint2 v = e < c ? sp[e] : make_uint2(0, 0);
+            if (e < c && __uint_as_float(v.x) > t) {
+                int id = (int)v.y;
+                if (perm)
+                    id = perm[id];
+                const float* yp = Y + (int64_t)id * d;
+                float acc = 0.f;
+                for (int i = 0; i < d; i++) {
+                    const float a = qp[i], b = __ldg(yp + i);
+                    if (IS_L2) {
+                        const float df = a - b;
+                        acc = fmaf(df, df, acc);
+                    } else {
+                        acc = fmaf(a, b, acc);
+                    }
+                }
+                if (!IS_L2)
+                    acc = -acc;
+                if (acc < bestD || (acc == bestD && id < bestI)) {
+                    bestD = acc;
+                    bestI = id;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(kFullMask, bestD, o);
+        const int oi = __shfl_xor_sync(kFullMask, bestI, o);
+        if (od < bestD || (od == bestD && oi < bestI)) {
+            bestD = od;
+            bestI = oi;
+        }
+    }
+    if (lane == 0) {
+        const bool ok = bestI != IdLimits<int>::max();
+        outD[q] = ok ? (IS_L2 ? bestD : -bestD) : (IS_L2 ? FLT_MAX : -FLT_MAX);
+        outI[q] = ok ? (idx_t)bestI : -1;
+        if (overflow || !ok)
+            flags[q] = 1;
+    }
+}
+
 // compact flagged query indices: list[0..count)
 __global__ void tc_collect_flags_kernel(const int* flags, int nq, int* list, int* count) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,12 +619,14 @@ int tcParts() {
 }
 
 template <bool DUMP>
-void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream) {
+void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, int grid, size_t smem, cudaStream_t stream, bool self = false) {
     // FB200_TC_DEBUG_SKIP=1 (timing experiments only): skip the filter, keep the TMEM loads
     static const bool dbg = getenv("FB200_TC_DEBUG_SKIP") && atoi(getenv("FB200_TC_DEBUG_SKIP")) != 0;
     const int parts = tcParts();
     auto kern = parts == 2 ? (dbg ? flat_tc_kernel<DUMP, 1, 2> : flat_tc_kernel<DUMP, 0, 2>)
                            : (dbg ? flat_tc_kernel<DUMP, 1, 4> : flat_tc_kernel<DUMP, 0, 4>);
+    if (self && !DUMP) // k = 1 streaming mode (self-tightening thresholds)
+        kern = parts == 2 ? flat_tc_kernel<false, 0, 2, true> : flat_tc_kernel<false, 0, 4, true>;
     CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTiming::begin("flat_tc", stream);
     kern<<<grid, tcThreads(parts), smem, stream>>>(mq, my, p);
@@ -593,7 +697,9 @@ void runFlatTcPrepareRows(
 
 bool flatTcSupported(int d, int k, int64_t n) {
     int dpad = (int)round_up(d, kKBlock);
-    return dpad <= 128 && k >= 1 && k <= 512 && n >= 32768 && n < (int64_t(1) << 31) - 512;
+    // k = 1 takes the streaming mode, which pays off from a few tiles on (coarse assignment against nlist >= 2048
+    // centroids during add / k-means); the round-based path needs a database worth several rounds
+    return dpad <= 128 && k >= 1 && k <= 512 && n >= (k == 1 ? 2048 : 32768) && n < (int64_t(1) << 31) - 512;
 }
 
 void runFlatTcScoresDebug(
@@ -712,7 +818,14 @@ void runFlatTcSearch(
         r0Tiles = std::max<int>((r0Tiles + nShards - 1) / nShards, std::max(2, (2 * kFrac + kTileN - 1) / kTileN));
     // queries per pass: bounds the candidate arena, whose largest user is the all-pass round 0
     // (512 KB per query pair and tile) -- 16384 queries at k = 100, up to 131072 for small k
-    const int64_t kQBatch = std::min<int64_t>(131072, std::max<int64_t>(16384, (int64_t)kPairM * 1024 / r0Tiles));
+    // k = 1 (k-means assignment, the coarse quantiser of an add): streaming mode -- one pass over all tiles with
+    // self-tightening per-thread thresholds (flat_tc_kernel SELF) and a fused select + exact re-rank
+    // (tc_argmin_finish_kernel); no rounds, no all-pass first round, no per-query sorted lists.
+    static const bool noStream = getenv("FB200_TC_NO_STREAM") && atoi(getenv("FB200_TC_NO_STREAM")) != 0;
+    const bool streaming = k == 1 && !shard && !noStream;
+    // streaming: a batch is a whole number of waves of the persistent grid (one 256-query unit per CTA and wave)
+    const int64_t kQBatch = streaming ? (int64_t)sms * kPairM * 4
+                                      : std::min<int64_t>(131072, std::max<int64_t>(16384, (int64_t)kPairM * 1024 / r0Tiles));
     for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
         const int64_t nq = std::min(kQBatch, nqAll - qb);
         const float* Qb = Q + qb * d;
@@ -723,8 +836,8 @@ void runFlatTcSearch(
         auto eps = res->temp(device, sizeof(float) * nq);
         auto thr = res->temp(device, sizeof(float) * nq);
         auto flags = res->temp(device, sizeof(int) * (nq + 1));
-        auto baseKey = res->temp(device, sizeof(float) * nq * LIST);
-        auto baseId = res->temp(device, sizeof(int) * nq * LIST);
+        auto baseKey = res->temp(device, streaming ? sizeof(float) : sizeof(float) * nq * LIST);
+        auto baseId = res->temp(device, streaming ? sizeof(int) : sizeof(int) * nq * LIST);
 
         CUDA_VERIFY(cudaMemsetAsync(scal.data, 0, sizeof(float) * 4, stream));
         CUDA_VERIFY(cudaMemsetAsync(flags.data, 0, sizeof(int) * (nq + 1), stream));
@@ -736,7 +849,7 @@ void runFlatTcSearch(
         tc_prepare_queries_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, stream>>>(
                 Qb, nq, d, dpad, sc + 1, c1, c2, yMaxNorm, q16.as<__half>(), eps.as<float>(), thr.as<float>());
         CUDA_CHECK_LAST();
-        {
+        if (!streaming) {
             int64_t cnt = nq * LIST;
             tc_init_base_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, stream>>>(
                     baseKey.as<float>(), baseId.as<int>(), cnt);
@@ -762,6 +875,8 @@ void runFlatTcSearch(
                                         : std::min<int64_t>(Tsched, (int64_t)(seen * g));
                 if (Tsched - end < end / 4)
                     end = Tsched; // do not leave a sliver for an extra round
+                if (streaming)
+                    end = Tsched; // k = 1: ONE pass, thresholds tighten themselves inside the kernel
                 int64_t tiles = end - seen;
                 // choose the slice count minimising (waves x tiles per slice)
                 int bestS = 1;
@@ -780,7 +895,10 @@ void runFlatTcSearch(
                 int64_t tps = ceil_div(tiles, bestS);
                 int S = (int)ceil_div(tiles, tps);
                 int cap;
-                if (seen == 0) {
+                if (streaming) {
+                    // a thread emits ~ln(columns it sees) running maxima plus the near-ties of the maximum
+                    cap = 64;
+                } else if (seen == 0) {
                     cap = (int)(tps * (kTileN / parts)); // everything passes in round 0
                 } else {
                     double expect = 1.5 * k * ((double)tps / (double)seen) / parts;
@@ -825,6 +943,7 @@ void runFlatTcSearch(
             p.bias = bias;
             p.tileMaxBias = tileMaxBias;
             p.thr = thr.as<float>();
+            p.eps = eps.as<float>();
             p.cand = arena.as<uint2>();
             p.cap = r.cap;
             p.candCount = counts.as<int>();
@@ -832,9 +951,26 @@ void runFlatTcSearch(
             p.dumpLd = 0;
             p.nq = (int)nq;
             if (p.tileBegin < p.tileEnd) {
-                launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream);
+                launchTc<false>(mapQ, mapY, p, std::min(p.numUnits, sms), sp.bytes, stream, streaming);
             } else { // this shard has no tiles in this round of the common schedule: no candidates
                 CUDA_VERIFY(cudaMemsetAsync(counts.data, 0, (size_t)p.numUnits * tcSegsPerUnit(parts) * sizeof(int), stream));
+            }
+            if (streaming) { // select + exact re-rank fused: one warp per query
+                const int fw = 8;
+                float* oD1 = outD + qb;
+                idx_t* oI1 = outI + qb;
+                KernelTiming::begin("tc_argmin_finish", stream);
+                if (metric == METRIC_L2)
+                    tc_argmin_finish_kernel<true><<<(unsigned)ceil_div(nq, fw), fw * 32, 0, stream>>>(
+                            (int)nq, d, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(), Qb, Y, perm,
+                            oD1, oI1, flags.as<int>());
+                else
+                    tc_argmin_finish_kernel<false><<<(unsigned)ceil_div(nq, fw), fw * 32, 0, stream>>>(
+                            (int)nq, d, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(), Qb, Y, perm,
+                            oD1, oI1, flags.as<int>());
+                KernelTiming::end("tc_argmin_finish", stream);
+                CUDA_CHECK_LAST();
+                continue;
             }
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
@@ -864,7 +1000,7 @@ void runFlatTcSearch(
         }
 
         // ---- exact re-rank
-        {
+        if (!streaming) {
             // (staging the 32 candidate rows of a step through shared memory with coalesced loads was
             // measured slower on B200: 0.91 ms vs 0.72 ms per 10k queries -- the per-lane row walk wins)
             const int rrWarps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / SmemTopK<int>::bytes(KL, 64)));

@@ -60,6 +60,7 @@ struct TcParams {
     const float* bias;  // [numTiles*256], -inf padded (read on the slow path only)
     const float* tileMaxBias; // [numTiles] max bias of the tile's rows (rows are stored sorted by norm)
     const float* thr;   // [nq]  pass if score > thr
+    const float* eps;   // [nq]  SELF mode (k = 1 streaming): a passing score v raises the thread's threshold to v - 2 eps
     uint2* cand;        // [numUnits*512][cap] (score bits, row)
     int cap;
     int* candCount;     // [numUnits*512]
@@ -80,14 +81,15 @@ __device__ __forceinline__ int perm_tile(const TcParams& p, int pos) {
 // negatives, bit for bit).  The fast path is therefore a pure FMNMX3 tree over raw accumulators --
 // no bias loads, no per-element FMA -- plus one FMA per 32 columns; the rare group whose bound beats
 // the threshold evaluates the exact test with biases read through L1/L2.
-template <bool DUMP>
+template <bool DUMP, bool SELF>
 __device__ __forceinline__ void epi_filter32(
         const TcParams& p,
         const uint32_t (&r)[32],
         int q,
         long long colBase, // global (sorted) row index of column 0 of this chunk
         float inv,
-        float thr,
+        float& thr,  // SELF: tightened in place (running maximum minus the slack)
+        float slack, // SELF: 2 * eps of this query
         float maxb,
         uint2* buf,
         int& cnt) {
@@ -122,6 +124,8 @@ __device__ __forceinline__ void epi_filter32(
                         if (cnt < p.cap)
                             buf[cnt] = make_uint2(__float_as_uint(v), rowBase + j);
                         cnt++;
+                        if (SELF) // k = 1: nothing scoring <= v - 2 eps can be the exact argmin any more
+                            thr = fmaxf(thr, nextafterf(v - slack, -CUDART_INF_F));
                     }
                 }
             }
@@ -131,7 +135,7 @@ __device__ __forceinline__ void epi_filter32(
 
 // 64 columns (two 32-column register sets) in one go: more independent work per warp for the
 // two-warps-per-scheduler configuration (PARTS = 2).
-template <bool DUMP>
+template <bool DUMP, bool SELF>
 __device__ __forceinline__ void epi_filter64(
         const TcParams& p,
         const uint32_t (&r0)[32],
@@ -139,15 +143,19 @@ __device__ __forceinline__ void epi_filter64(
         int q,
         long long colBase,
         float inv,
-        float thr,
+        float& thr,
+        float slack,
         float maxb,
         uint2* buf,
         int& cnt) {
-    epi_filter32<DUMP>(p, r0, q, colBase, inv, thr, maxb, buf, cnt);
-    epi_filter32<DUMP>(p, r1, q, colBase + 32, inv, thr, maxb, buf, cnt);
+    epi_filter32<DUMP, SELF>(p, r0, q, colBase, inv, thr, slack, maxb, buf, cnt);
+    epi_filter32<DUMP, SELF>(p, r1, q, colBase + 32, inv, thr, slack, maxb, buf, cnt);
 }
 
-template <bool DUMP, int DBG, int PARTS>
+// SELF (k = 1 streaming mode, used for k-means assignment): one pass over all tiles, every epilogue thread keeps
+// a running "best approximate score minus 2 eps" threshold for its two queries and emits only the candidates
+// that beat it -- about ln(columns per thread) plus the near-ties of the maximum.
+template <bool DUMP, int DBG, int PARTS, bool SELF = false>
 __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
         const __grid_constant__ CUtensorMap mapQ,
         const __grid_constant__ CUtensorMap mapY,
@@ -287,8 +295,10 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
             // per-thread filter state for its two queries (one per query tile of the pair)
             const int q0 = pair * kPairM + row;
             const int q1 = q0 + kTileM;
-            const float thr0 = (!DUMP && q0 < p.nq) ? p.thr[q0] : CUDART_INF_F;
-            const float thr1 = (!DUMP && q1 < p.nq) ? p.thr[q1] : CUDART_INF_F;
+            float thr0 = (!DUMP && q0 < p.nq) ? p.thr[q0] : CUDART_INF_F;
+            float thr1 = (!DUMP && q1 < p.nq) ? p.thr[q1] : CUDART_INF_F;
+            const float slack0 = (SELF && q0 < p.nq) ? 2.f * p.eps[q0] : 0.f;
+            const float slack1 = (SELF && q1 < p.nq) ? 2.f * p.eps[q1] : 0.f;
             const long long seg0 = ((long long)u * kPairM + row) * PARTS + half;
             const long long seg1 = ((long long)u * kPairM + kTileM + row) * PARTS + half;
             uint2* buf0 = DUMP ? nullptr : p.cand + seg0 * p.cap;
@@ -317,7 +327,8 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const int q = h ? q1 : q0;
-                    const float thr = h ? thr1 : thr0;
+                    float thr = h ? thr1 : thr0;
+                    const float slack = h ? slack1 : slack0;
                     uint2* buf = h ? buf1 : buf0;
                     int cnt = h ? cnt1 : cnt0;
                     const uint32_t acc = lane_acc + (uint32_t)h * kTileN;
@@ -340,15 +351,20 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                         }
                         if (DBG == 0) {
                             if constexpr (PARTS == 2)
-                                epi_filter64<DUMP>(p, a0, a1, q, colBase + blk * 64, inv, thr, maxb, buf, cnt);
+                                epi_filter64<DUMP, SELF>(p, a0, a1, q, colBase + blk * 64, inv, thr, slack, maxb, buf, cnt);
                             else
-                                epi_filter32<DUMP>(p, a0, q, colBase + blk * 32, inv, thr, maxb, buf, cnt);
+                                epi_filter32<DUMP, SELF>(p, a0, q, colBase + blk * 32, inv, thr, slack, maxb, buf, cnt);
                         }
                     }
-                    if (h)
+                    if (h) {
                         cnt1 = cnt;
-                    else
+                        if (SELF)
+                            thr1 = thr;
+                    } else {
                         cnt0 = cnt;
+                        if (SELF)
+                            thr0 = thr;
+                    }
                 }
                 tphase ^= 1;
             }

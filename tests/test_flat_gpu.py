@@ -230,3 +230,47 @@ def test_memory_info_and_oom(res):
     assert big.ntotal == 100
     D, I = idx.search(np.zeros((2, 16), dtype=np.float32), 3)
     assert I.shape == (2, 3)
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+@pytest.mark.parametrize("N,d,nq", [(4096, 128, 3000), (70000, 96, 5000), (2048, 64, 17), (300000, 32, 700)])
+def test_streaming_argmin_equals_exact_path(res, N, d, nq, metric):
+    """k = 1 takes the streaming tcgen05 mode (self-tightening thresholds, fused select + re-rank): the k-means
+    assignment path.  Must be indistinguishable from the exact kernel, ids and distances."""
+    import torch
+
+    import faiss_b200 as fb
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(N + d)
+    xb = torch.rand(N, d, device="cuda", generator=g)
+    xq = torch.rand(nq, d, device="cuda", generator=g)
+    idx = fb.GpuIndexFlat(res, d, metric)
+    idx.add(xb)
+    D, I = idx.search(xq, 1)
+    assert idx.lastSearchInfo()["tensor_cores"] == 1
+    idx.setUseTensorCores(False)
+    De, Ie = idx.search(xq, 1)
+    assert torch.equal(I, Ie) and torch.equal(D, De)
+
+
+def test_streaming_argmin_with_masses_of_ties(res):
+    """duplicated rows: every query has hundreds of exact ties for the minimum -- more than a candidate segment
+    holds -- so the certificate fails over to the exact kernel; the answer is still the smallest id"""
+    import torch
+
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(11)
+    base = np.floor(rs.rand(64, 32) * 8).astype(np.float32)
+    xb = np.tile(base, (1500, 1))  # 96000 rows, each distinct row 1500 times
+    xq = base[rs.randint(0, 64, size=200)] + 0.0
+    idx = fb.GpuIndexFlatL2(res, 32)
+    idx.add(xb)
+    D, I = idx.search(xq, 1)
+    info = idx.lastSearchInfo()
+    assert info["tensor_cores"] == 1
+    idx.setUseTensorCores(False)
+    De, Ie = idx.search(xq, 1)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+    assert (D == 0).all() and (I < 64).all()
