@@ -709,6 +709,12 @@ def main():
     ex_ms, mg_ms, ex_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
     fb.lib.faiss_b200_kernel_timing_collect(b"shards_exchange", ctypes.byref(ex_ms), ctypes.byref(ex_n))
     fb.lib.faiss_b200_kernel_timing_collect(b"shards_merge", ctypes.byref(mg_ms), ctypes.byref(ex_n))
+    breakdown = {}
+    for nm in (b"tc_select", b"tc_pool", b"tc_rerank"):
+        v, c = ctypes.c_double(), ctypes.c_int()
+        fb.lib.faiss_b200_kernel_timing_collect(nm, ctypes.byref(v), ctypes.byref(c))
+        breakdown[nm.decode() + "_ms"] = v.value / steps
+        breakdown[nm.decode() + "_launches"] = c.value // steps
     fb.lib.faiss_b200_kernel_timing(0)
     clocks = sampler.stop() if rank == 0 else None
     info = index.lastSearchInfo()
@@ -763,7 +769,9 @@ def main():
                "e2e": {"value": NQ / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": NQ * DIM * 4, "d2h_bytes_per_step": NQ * K * 12},
                "gpu_launches": int(launches), "roofline": roof,
-               "search_info": info}
+               "search_info": info,
+               "step_breakdown_ms": dict(breakdown, flat_tc_ms=(tc_ms.value / steps if tc_n.value else None),
+                                         note="rank 0, CUDA events around each launch (threshold select, cross-rank pooling, exact re-rank)")}
         if world > 1:
             out["collective_ms"] = ex_ms.value / steps  # rank 0's all-gather (includes waiting for the slowest rank)
             out["merge_ms"] = mg_ms.value / steps

@@ -11,7 +11,7 @@ One process per GPU.  Per rank: its contiguous slice of the database and of the 
     (k*d sums | k counts | objective); PQ codebooks trained on rank 0's residuals and broadcast.
   * add: device-side assign -> residual -> PQ encode -> append, shard-local ids.
   * search: every query to every shard, ONE all-gather of the per-shard [nq, k] (fp32 | int64) + device
-    merge (`ShardedSearcher`), ids translated like successive_ids.
+    merge (`DistributedIndexShards`, NCCL communicator owned by the C++ resources), ids translated like successive_ids.
 Prints one JSON line (rank 0).  configs[4] itself is N=1e9 on 8 GPUs (125M vectors per GPU); the defaults
 here are sized per GPU the same way (--ntotal defaults to 125M x world).
 """
@@ -71,12 +71,17 @@ def main():
 
     import faiss_b200 as fb
     from bench import ClockSampler, peaks
-    from faiss_b200.distributed import ShardedSearcher, shard_bounds, sharded_kmeans
+    from faiss_b200.distributed import merge_host, shard_bounds, sharded_kmeans
 
     N = args.ntotal or 125_000_000 * world
     d, nlist, M, nq, k = args.d, args.nlist, args.m, args.nq, args.k
     res = fb.StandardGpuResources()
     res.setDefaultStream(local_rank, torch.cuda.current_stream(dev).cuda_stream)
+    # the search path's NCCL communicator belongs to the library's resources object (C++); torch.distributed hands
+    # the 128-byte id around and serves the Python-level k-means all-reduce
+    ids = [fb.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, device=dev)
+    res.ncclInitRank(local_rank, world, rank, ids[0])
 
     CH = 1_000_000
 
@@ -152,7 +157,9 @@ def main():
     g = torch.Generator(device=dev)
     g.manual_seed(1235)
     xq = torch.rand((nq, d), dtype=torch.float32, device=dev, generator=g)
-    searcher = ShardedSearcher(lambda x, kk: index.search(x, kk), r1 - r0, fb.METRIC_L2, res=res, device=local_rank)
+    # IndexShards with one shard per rank behind the C ABI: ONE grouped ncclAllGather + device merge
+    searcher = fb.DistributedIndexShards(res, index, successive_ids=True)
+    assert searcher.ntotal == N, (searcher.ntotal, N)
 
     for _ in range(max(3, args.warmup)):
         D, I = searcher.search(xq, k)
@@ -185,6 +192,22 @@ def main():
     probes = torch.cdist(xq, cent_d).topk(args.nprobe, dim=1, largest=False).indices.cpu().numpy()
     scanned = torch.tensor([float(lens[probes].sum())], dtype=torch.float64, device=dev)
     dist.all_reduce(scanned, op=dist.ReduceOp.SUM)
+    # ---- parity of the collective path (outside the timed region): the merged result of a query sample must equal
+    # the reference merge rule (merge_knn_results semantics, host) applied to every rank's LOCAL result
+    ns = min(nq, 256)
+    lD, lI = index.search(xq[:ns].contiguous(), k)
+    lI = torch.where(lI >= 0, lI + r0, lI)
+    gD = [torch.empty_like(lD) for _ in range(world)]
+    gI = [torch.empty_like(lI) for _ in range(world)]
+    dist.all_gather(gD, lD)
+    dist.all_gather(gI, lI)
+    parity = None
+    if rank == 0:
+        hD, hI = merge_host(torch.stack(gD).cpu().numpy(), torch.stack(gI).cpu().numpy(), k, fb.METRIC_L2)
+        parity = {"queries": ns, "ids_equal": bool(np.array_equal(hI, I[:ns].cpu().numpy())),
+                  "distances_equal": bool(np.array_equal(hD, D[:ns].cpu().numpy())),
+                  "what": "NCCL all-gather + device merge == host merge_knn_results of the %d per-rank results" % world}
+        parity["ok"] = parity["ids_equal"] and parity["distances_equal"]
     if rank == 0:
         clocks = sampler.stop()
         pk, src = peaks()
@@ -197,7 +220,7 @@ def main():
                    "kmeans": {"points": n_train, "niter": args.niter, "train_s": train_s, "s_per_iter": train_s / args.niter,
                               "allreduce_bytes_per_iter": 4 * (nlist * d + nlist + 1), "objective_first_last": [float(objs[0]), float(objs[-1])]},
                    "add_s": add_s, "add_vec_per_s_per_gpu": (r1 - r0) / add_s, "allgather_bytes_per_rank_per_step": nq * k * 12},
-               "clocks": clocks,
+               "clocks": clocks, "parity_check": parity,
                "roofline": {"bound": "hbm", "unit": "GB/s", "peak": float(pk["hbm_gbs"]) * world, "peak_source": src + " copy bandwidth x n_gpus",
                             "algorithmic_bytes_per_step": alg, "scan_ms_per_step_max_over_ranks": scan_ms,
                             "achieved": alg / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,

@@ -972,6 +972,7 @@ void runFlatTcSearch(
                 CUDA_CHECK_LAST();
                 continue;
             }
+            KernelTiming::begin("tc_select", stream);
             tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
                     (int)nq,
                     k,
@@ -988,13 +989,16 @@ void runFlatTcSearch(
                     flags.as<int>(),
                     shard ? contrib.as<float>() : nullptr,
                     kFrac);
+            KernelTiming::end("tc_select", stream);
             CUDA_CHECK_LAST();
             if (shard) {
+                KernelTiming::begin("tc_pool", stream);
                 // ONE small all-reduce per round (2 floats per query): every shard then filters against a
                 // threshold certified by the pooled evidence of all shards
                 shard->comm->allReduceMax(contrib.as<float>(), (size_t)2 * nq, stream);
                 tc_pooled_thr_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(
                         (int)nq, contrib.as<float>(), eps.as<float>(), thr.as<float>());
+                KernelTiming::end("tc_pool", stream);
                 CUDA_CHECK_LAST();
             }
         }
@@ -1013,10 +1017,12 @@ void runFlatTcSearch(
                         (int)nq, d, k, LIST, KL, Qb, Y, perm, baseId.as<int>(), baseKey.as<float>(),
                         shard ? thr.as<float>() : nullptr, oD, oI);
             };
+            KernelTiming::begin("tc_rerank", stream);
             if (metric == METRIC_L2)
                 launchRr(tc_rerank_kernel<true>);
             else
                 launchRr(tc_rerank_kernel<false>);
+            KernelTiming::end("tc_rerank", stream);
             CUDA_CHECK_LAST();
         }
 
