@@ -6,9 +6,9 @@ one node (IndexShards semantics), coarse quantiser trained by sharded k-means.
       bench_shards.py --gpus N [--ntotal 1000000000 --d 96 --nlist 65536 --m 32 --nprobe 32]
 
 One process per GPU.  Per rank: its contiguous slice of the database and of the training set.
-  * train: `faiss_b200.distributed.sharded_kmeans` -- Flat k=1 assignment on the tcgen05 path against the
-    replicated centroid table, privatised partial sums, ONE packed NCCL all-reduce per iteration
-    (k*d sums | k counts | objective); PQ codebooks trained on rank 0's residuals and broadcast.
+  * train: `faiss_b200.kmeans_sharded` (C++, faiss_b200_kmeans_sharded) -- Flat k=1 assignment on the tcgen05
+    streaming path against the replicated centroid table, deterministic local partial sums, ONE packed NCCL
+    all-reduce per iteration (k*d sums | k counts | objective); PQ codebooks trained on rank 0's residuals and broadcast.
   * add: device-side assign -> residual -> PQ encode -> append, shard-local ids.
   * search: every query to every shard, ONE all-gather of the per-shard [nq, k] (fp32 | int64) + device
     merge (`DistributedIndexShards`, NCCL communicator owned by the C++ resources), ids translated like successive_ids.
@@ -71,7 +71,7 @@ def main():
 
     import faiss_b200 as fb
     from bench import ClockSampler, peaks
-    from faiss_b200.distributed import merge_host, shard_bounds, sharded_kmeans
+    from faiss_b200.distributed import merge_host, shard_bounds
 
     N = args.ntotal or 125_000_000 * world
     d, nlist, M, nq, k = args.d, args.nlist, args.m, args.nq, args.k
@@ -103,26 +103,19 @@ def main():
     n_train = min(N, nlist * args.ppc)
     t0, t1 = shard_bounds(n_train, rank, world)
     xt = gen(t0, t1, 500_000)
-    cq = fb.GpuIndexFlatL2(res, d, device=local_rank)
-
-    def local_assign(cent, x):
-        cq.reset()
-        cq.add(cent)
-        D, I = cq.search(x, 1)
-        return D[:, 0], I[:, 0].contiguous()
-
-    def local_accumulate(x, assign, kk):
-        return fb.kmeans_accumulate(res, x, assign, kk, device=local_rank)
-
     torch.cuda.synchronize()
     dist.barrier()
     tt = time.time()
-    cent, objs = sharded_kmeans(xt, nlist, args.niter, local_assign, local_accumulate, seed=1234)
+    # C++ sharded k-means behind the C ABI: local tcgen05 k=1 assignment (streaming mode), deterministic local
+    # partial sums, ONE packed ncclAllReduce per iteration on the library's own communicator
+    cent_np, objs, kstats = fb.kmeans_sharded(res, xt, nlist, niter=args.niter, seed=1234, device=local_rank)
+    cent = torch.from_numpy(cent_np).to(dev)
     torch.cuda.synchronize()
     dist.barrier()
     train_s = time.time() - tt
-    log("[rank %d] k-means %d x %d-d on %d points (%d local): %.2f s, objective %.4g -> %.4g" % (
-        rank, nlist, d, n_train, t1 - t0, train_s, objs[0], objs[-1]))
+    if rank == 0:
+        log("[rank %d] k-means %d x %d-d on %d points (%d local): %.2f s, objective %.4g -> %.4g, %s" % (
+            rank, nlist, d, n_train, t1 - t0, train_s, objs[0], objs[-1], kstats))
     assert all(objs[i + 1] <= objs[i] * 1.0001 for i in range(len(objs) - 1)), "objective must not increase"
 
     # ---------------------------------------------------------------- PQ codebooks: rank 0 trains, broadcast
@@ -137,7 +130,7 @@ def main():
     if rank != 0:
         index.setPQCentroids(pq.cpu().numpy())
         index.setIsTrained(True)
-    del xt, cq
+    del xt
 
     # ---------------------------------------------------------------- add this rank's shard
     r0, r1 = shard_bounds(N, rank, world)
@@ -218,7 +211,7 @@ def main():
                "config": {"workload": "IndexShards x%d of GpuIndexIVFPQ: N=%d (%d per GPU) d=%d nlist=%d M=%d nbits=8 nprobe=%d nq=%d k=%d (BASELINE configs[4] per-GPU shape)" % (
                    world, N, N // world, d, nlist, M, args.nprobe, nq, k),
                    "kmeans": {"points": n_train, "niter": args.niter, "train_s": train_s, "s_per_iter": train_s / args.niter,
-                              "allreduce_bytes_per_iter": 4 * (nlist * d + nlist + 1), "objective_first_last": [float(objs[0]), float(objs[-1])]},
+                              "allreduce_bytes_per_iter": 4 * (nlist * d + nlist + 1), "objective_first_last": [float(objs[0]), float(objs[-1])], "stats": kstats},
                    "add_s": add_s, "add_vec_per_s_per_gpu": (r1 - r0) / add_s, "allgather_bytes_per_rank_per_step": nq * k * 12},
                "clocks": clocks, "parity_check": parity,
                "roofline": {"bound": "hbm", "unit": "GB/s", "peak": float(pk["hbm_gbs"]) * world, "peak_source": src + " copy bandwidth x n_gpus",

@@ -588,6 +588,24 @@ def kmeans_ex(res, x, k, niter=25, seed=1234, max_points_per_centroid=256, metri
     return cent, obj
 
 
+def kmeans_sharded(res, x_local, k, niter=25, seed=1234, device=0):
+    """Collective: k-means over the rows of ALL ranks of the device's NCCL communicator (this rank passes its own
+    rows; rank order = row order).  Returns (centroids [k, d] identical on every rank, objective per iteration,
+    stats dict)."""
+    x_local = _as_f32(x_local)
+    n, d = x_local.shape
+    cent = np.empty((k, d), dtype=np.float32)
+    obj = np.zeros(niter, dtype=np.float32)
+    st = (ctypes.c_double * 4)()
+    check(
+        lib.faiss_b200_kmeans_sharded(
+            res._h, int(device), ctypes.c_size_t(d), ctypes.c_size_t(n), ctypes.c_size_t(k), _ptr(x_local, _c_f), int(niter), int(seed),
+            _ptr(cent, _c_f), _ptr(obj, _c_f), st,
+        )
+    )
+    return cent, obj, {"total_s": st[0], "search_update_allreduce_s": st[1], "split_clusters_s": st[2], "nsplit": int(st[3])}
+
+
 def pq_train(res, x, M, niter=25, seed=1234, device=0):
     """faiss::ProductQuantizer::train (M independent 256-centroid k-means); returns [M, 256, d/M]."""
     x = _as_f32(x)

@@ -693,6 +693,51 @@ int faiss_b200_kmeans_ex(
     CATCH_AND_HANDLE
 }
 
+int faiss_b200_kmeans_sharded(
+        FaissStandardGpuResources* r,
+        int device,
+        size_t d,
+        size_t n_local,
+        size_t k,
+        const float* x_local,
+        int niter,
+        int seed,
+        float* centroids_out,
+        float* obj_out,
+        double* stats_out) {
+    try {
+        auto res = RES(r);
+        res->initializeForDevice(device);
+        auto comm = res->getCommunicator(device);
+        FB_THROW_IF_NOT_MSG(comm != nullptr, "no NCCL communicator for this device: call ncclInitRank / ncclInitAll first");
+        ClusteringParameters cp;
+        if (niter > 0)
+            cp.niter = niter;
+        if (seed >= 0)
+            cp.seed = seed;
+        Clustering clus((int)d, (int)k, cp);
+        GpuIndexFlatConfig fc;
+        fc.device = device;
+        GpuIndexFlatL2 index(res, (int)d, fc);
+        clus.trainSharded((idx_t)n_local, x_local, index, *comm);
+        memcpy(centroids_out, clus.centroids.data(), sizeof(float) * d * k);
+        if (obj_out) {
+            for (size_t i = 0; i < clus.iteration_stats.size() && (int)i < cp.niter; i++)
+                obj_out[i] = clus.iteration_stats[i].obj;
+        }
+        if (stats_out) {
+            stats_out[0] = clus.iteration_stats.empty() ? 0 : clus.iteration_stats.back().time;
+            stats_out[1] = clus.iteration_stats.empty() ? 0 : clus.iteration_stats.back().time_search;
+            stats_out[2] = clus.splitSeconds;
+            double ns = 0;
+            for (auto& s : clus.iteration_stats)
+                ns += s.nsplit;
+            stats_out[3] = ns;
+        }
+    }
+    CATCH_AND_HANDLE
+}
+
 int faiss_b200_pq_train(
         FaissStandardGpuResources* r,
         int device,

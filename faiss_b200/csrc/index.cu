@@ -697,6 +697,144 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
     }
 }
 
+namespace {
+__global__ void scatter_rows_kernel(const float* src, const int* srcRow, const int* dstRow, int64_t n, int d, float* dst) {
+    const int64_t i = blockIdx.x;
+    if (i >= n)
+        return;
+    for (int j = threadIdx.x; j < d; j += blockDim.x)
+        dst[(int64_t)dstRow[i] * d + j] = src[(int64_t)srcRow[i] * d + j];
+}
+__global__ void store_obj_kernel(const double* acc, float* out) {
+    *out = (float)*acc;
+}
+} // namespace
+
+void Clustering::trainSharded(idx_t nLocal, const float* x_in, GpuIndexFlat& index, const Communicator& comm) {
+    FB_THROW_IF_NOT_FMT((size_t)index.d == d, "Index dimension %d not the same as data dimension %d", index.d, (int)d);
+    FB_THROW_IF_NOT_MSG(!frozen_centroids, "Clustering: frozen_centroids (input centroids) is not supported by faiss_b200");
+    FB_THROW_IF_NOT_MSG(nredo == 1, "sharded clustering supports nredo == 1");
+    GpuResources* res = index.getResources().get();
+    const int device = index.getDevice();
+    DeviceScope scope(device);
+    cudaStream_t stream = res->getDefaultStream(device);
+    const double t0 = now_ms();
+    splitSeconds = 0;
+
+    DeviceView<float> xall(res, device, x_in, (size_t)nLocal * d, stream);
+    const float* x = xall.ptr;
+    std::vector<int64_t> sizes = comm.allGatherHostI64(nLocal, stream);
+    idx_t nTotal = 0, off = 0;
+    for (int r = 0; r < comm.size(); r++) {
+        if (r < comm.rank())
+            off += sizes[r];
+        nTotal += sizes[r];
+    }
+    FB_THROW_IF_NOT_FMT(
+            nTotal >= (idx_t)k,
+            "Number of training points (%ld) should be at least as large as number of clusters (%zd)",
+            (long)nTotal,
+            k);
+    FB_THROW_IF_NOT_MSG(nTotal <= (idx_t)0x7fffffff, "Dataset too large for the reference's int permutation");
+
+    centroids.resize(d * k);
+    const size_t packedLen = k * d + k + 1; // sums | counts | objective
+    auto cDev = res->device_alloc(device, sizeof(float) * k * d, AllocType::Other);
+    auto packed = res->device_alloc(device, sizeof(float) * packedLen, AllocType::Other);
+    auto assign = res->device_alloc(device, sizeof(idx_t) * std::max<idx_t>(nLocal, 1), AllocType::Other);
+    auto dis = res->device_alloc(device, sizeof(float) * std::max<idx_t>(nLocal, 1), AllocType::Other);
+    auto objBuf = res->device_alloc(device, sizeof(double), AllocType::Other);
+
+    // ---- initial centroids = rows rand_perm(nTotal, seed + 1)[:k] of the concatenated set: every row is owned by
+    // exactly one rank, which writes it into a zeroed table; the all-reduce assembles the table everywhere
+    {
+        std::vector<int> perm(nTotal);
+        rand_perm(perm.data(), nTotal, (int64_t)seed + 1);
+        std::vector<int> srcRow, dstRow;
+        for (size_t i = 0; i < k; i++) {
+            const idx_t g = perm[i];
+            if (g >= off && g < off + nLocal) {
+                srcRow.push_back((int)(g - off));
+                dstRow.push_back((int)i);
+            }
+        }
+        CUDA_VERIFY(cudaMemsetAsync(cDev.data, 0, sizeof(float) * k * d, stream));
+        if (!srcRow.empty()) {
+            auto sd = res->temp(device, sizeof(int) * srcRow.size() * 2);
+            CUDA_VERIFY(cudaMemcpyAsync(sd.data, srcRow.data(), sizeof(int) * srcRow.size(), cudaMemcpyHostToDevice, stream));
+            CUDA_VERIFY(cudaMemcpyAsync(sd.as<int>() + srcRow.size(), dstRow.data(), sizeof(int) * srcRow.size(), cudaMemcpyHostToDevice, stream));
+            scatter_rows_kernel<<<(unsigned)srcRow.size(), std::min<int>(256, (int)d), 0, stream>>>(
+                    x, sd.as<int>(), sd.as<int>() + srcRow.size(), (int64_t)srcRow.size(), (int)d, cDev.as<float>());
+            CUDA_CHECK_LAST();
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+        }
+        comm.allReduceSum(cDev.as<float>(), k * d, stream);
+        runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
+    }
+    if (index.ntotal != 0)
+        index.reset();
+    index.add(k, cDev.as<float>());
+
+    std::vector<float> hassign(k);
+    double t_search_tot = 0;
+    for (int it = 0; it < niter; it++) {
+        const double t0s = now_ms();
+        if (nLocal > 0)
+            index.searchDevice(nLocal, x, 1, dis.as<float>(), assign.as<idx_t>());
+        CUDA_VERIFY(cudaMemsetAsync(objBuf.data, 0, sizeof(double), stream));
+        CUDA_VERIFY(cudaMemsetAsync(packed.data, 0, sizeof(float) * packedLen, stream));
+        if (nLocal > 0) {
+            sum_kernel<<<296, 256, 0, stream>>>(dis.as<float>(), nLocal, objBuf.as<double>());
+            CUDA_CHECK_LAST();
+            runKmeansAccumulate(x, assign.as<idx_t>(), nLocal, (int)d, (int64_t)k, packed.as<float>(), packed.as<float>() + k * d, stream);
+        }
+        store_obj_kernel<<<1, 1, 0, stream>>>(objBuf.as<double>(), packed.as<float>() + k * d + k);
+        CUDA_CHECK_LAST();
+        // ONE packed reduction per iteration
+        comm.allReduceSum(packed.as<float>(), packedLen, stream);
+        runKmeansFinalize(packed.as<float>(), packed.as<float>() + k * d, (int64_t)k, (int)d, cDev.as<float>(), stream);
+        float hobj = 0;
+        CUDA_VERIFY(cudaMemcpyAsync(hassign.data(), packed.as<float>() + k * d, sizeof(float) * k, cudaMemcpyDeviceToHost, stream));
+        CUDA_VERIFY(cudaMemcpyAsync(&hobj, packed.as<float>() + k * d + k, sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CUDA_VERIFY(cudaStreamSynchronize(stream));
+        t_search_tot += now_ms() - t0s;
+        int nsplit = 0;
+        double tot = 0, uf = 0;
+        bool anyEmpty = false;
+        for (size_t c = 0; c < k; c++) {
+            tot += hassign[c];
+            uf += (double)hassign[c] * hassign[c];
+            anyEmpty |= hassign[c] == 0;
+        }
+        const double imb = tot > 0 ? uf * k / (tot * tot) : 0;
+        if (anyEmpty) {
+            // identical inputs and a fixed-seed generator: every rank computes the same split
+            const double ts = now_ms();
+            CUDA_VERIFY(cudaMemcpyAsync(centroids.data(), cDev.data, sizeof(float) * k * d, cudaMemcpyDeviceToHost, stream));
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+            nsplit = split_clusters(d, k, nTotal, hassign.data(), centroids.data());
+            CUDA_VERIFY(cudaMemcpyAsync(cDev.data, centroids.data(), sizeof(float) * k * d, cudaMemcpyHostToDevice, stream));
+            splitSeconds += (now_ms() - ts) / 1000.0;
+        }
+        iteration_stats.push_back({hobj, (now_ms() - t0) / 1000.0, t_search_tot / 1000.0, imb, nsplit});
+        if (verbose) {
+            printf("  Iteration %d (%.2f s, search %.2f s): objective=%g imbalance=%.3f nsplit=%d\n",
+                   it, (now_ms() - t0) / 1000.0, t_search_tot / 1000.0, hobj, imb, nsplit);
+            fflush(stdout);
+        }
+        runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
+        index.reset();
+        index.add(k, cDev.as<float>());
+        if (it > 0) {
+            const float prev = iteration_stats[iteration_stats.size() - 2].obj;
+            if (prev != 0 && std::fabs((double)prev - (double)hobj) / std::fabs((double)prev) <= 0.0)
+                break;
+        }
+    }
+    CUDA_VERIFY(cudaMemcpyAsync(centroids.data(), cDev.data, sizeof(float) * k * d, cudaMemcpyDeviceToHost, stream));
+    CUDA_VERIFY(cudaStreamSynchronize(stream));
+}
+
 // ------------------------------------------------------------------------------------------
 // IvfLists
 // ------------------------------------------------------------------------------------------

@@ -180,6 +180,13 @@ FB200_API int faiss_b200_kmeans(FaissStandardGpuResources* res, int device, size
 /* same with the assignment metric and ClusteringParameters::spherical (what GpuIndexIVF uses for
    METRIC_INNER_PRODUCT, faiss/gpu/GpuIndexIVF.cu:72-76; post_process_centroids, faiss/Clustering.cpp:35-45) */
 FB200_API int faiss_b200_kmeans_ex(FaissStandardGpuResources* res, int device, size_t d, size_t n, size_t k, const float* x, int niter, int seed, int max_points_per_centroid, FaissMetricType metric, int spherical, float* centroids_out, float* obj_out);
+/* Lloyd k-means with the training set sharded over the ranks of the device's NCCL communicator (collective call:
+   every rank passes its own rows, rank order = row order of the concatenated set; faiss/Clustering.cpp:60-380 on the
+   concatenation): local Flat k=1 assignment, deterministic local partial sums, ONE packed ncclAllReduce
+   per iteration (k*d sums | k counts | objective), identical split_clusters on every rank.  centroids_out host [k*d]
+   (identical on all ranks); stats_out (optional, 4 doubles): total s, s in search+update+all-reduce, s in
+   split_clusters, number of splits */
+FB200_API int faiss_b200_kmeans_sharded(FaissStandardGpuResources* res, int device, size_t d, size_t n_local, size_t k, const float* x_local, int niter, int seed, float* centroids_out, float* obj_out, double* stats_out);
 /* ProductQuantizer::train, Train_default (faiss/impl/ProductQuantizer.cpp:130-195): M independent 256-centroid
    k-means on the column slices of x [n,d] (host or device); centroids_out host [M][256][d/M] */
 FB200_API int faiss_b200_pq_train(FaissStandardGpuResources* res, int device, size_t d, size_t M, size_t n, const float* x, int niter, int seed, float* centroids_out);

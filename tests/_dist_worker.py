@@ -91,6 +91,15 @@ def main():
         uD, uI = full.search(q3, k3)
         out["ivfflat_idmod"] = {"ids_equal": bool(np.array_equal(I, uI)), "distances_equal": bool(np.array_equal(D, uD))}
     del sh, ivf
+    # ---- sharded k-means (C++, one packed all-reduce per iteration) == the single-process algorithm on the
+    # concatenated set: integer-valued points make every partial sum exact, so the centroids must be identical
+    xk = np.floor(rs.rand(24_000, 16) * 32).astype(np.float32)
+    r0, r1 = rank * 24_000 // world, (rank + 1) * 24_000 // world
+    cent, obj, st = fb.kmeans_sharded(res, xk[r0:r1], 50, niter=6, seed=321, device=local)
+    if rank == 0:
+        c1, o1 = fb.kmeans(res, xk, 50, niter=6, seed=321, max_points_per_centroid=1 << 20, device=local)
+        out["kmeans_sharded"] = {"ids_equal": bool(np.array_equal(cent, c1)), "distances_equal": bool(np.allclose(obj, o1, rtol=1e-5)),
+                                 "max_abs_diff": float(np.abs(cent - c1).max())}
     dist.barrier()
     if rank == 0:
         print("RESULT " + json.dumps(out), flush=True)

@@ -68,6 +68,6 @@ def test_distributed_index_shards_processes(world):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
     out = json.loads(line[len("RESULT "):])
     assert out["world"] == world
-    for name in ("flat_float", "flat_int", "flat_ip_small", "ivfflat_idmod"):
+    for name in ("flat_float", "flat_int", "flat_ip_small", "ivfflat_idmod", "kmeans_sharded"):
         assert out[name]["ids_equal"] and out[name]["distances_equal"], (name, out[name])
     assert out["flat_float"]["tensor_cores"] == 1 and out["flat_float"]["device_queries_equal"]
