@@ -210,7 +210,8 @@ class Index:
         self._use_torch_stream(x, ids)
         check(lib.faiss_Index_add_with_ids(self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f), _ptr(ids, _c_i64)))
 
-    def search(self, x, k, D=None, I=None):
+    def search(self, x, k, D=None, I=None, params=None):
+        """params: a SearchParametersIVF (per-call nprobe) or None -- faiss::Index::search(..., params)"""
         x = self._check_x(x)
         n = x.shape[0]
         if D is None:
@@ -218,6 +219,13 @@ class Index:
         if I is None:
             I = _empty_like_residency(x, (n, k), np.int64)
         self._use_torch_stream(x, D, I)
+        if params is not None:
+            check(
+                lib.faiss_Index_search_with_params(
+                    self._h, ctypes.c_int64(n), _ptr(x, _c_f), ctypes.c_int64(k), params._h, _ptr(D, _c_f), _ptr(I, _c_i64)
+                )
+            )
+            return D, I
         check(
             lib.faiss_Index_search(
                 self._h, ctypes.c_int64(n), _ptr(x, _c_f), ctypes.c_int64(k), _ptr(D, _c_f), _ptr(I, _c_i64)
@@ -269,6 +277,34 @@ class Index:
             )
         )
         return out
+
+
+class SearchParametersIVF:
+    """faiss::SearchParametersIVF (faiss/IndexIVF.h:68-90): per-call nprobe; max_codes must stay 0 on the GPU."""
+
+    def __init__(self, nprobe=1, max_codes=0):
+        self._h = ctypes.c_void_p()
+        check(lib.faiss_SearchParametersIVF_new_with(ctypes.byref(self._h), ctypes.c_size_t(int(nprobe)), ctypes.c_size_t(int(max_codes))))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            lib.faiss_SearchParameters_free(self._h)
+            self._h = None
+
+
+_INTERRUPT_CB = None
+
+
+def set_interrupt_callback(fn):
+    """faiss::InterruptCallback: fn() -> truthy to make the running call fail with 'computation interrupted'; None clears."""
+    global _INTERRUPT_CB
+    proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
+    if fn is None:
+        lib.faiss_b200_set_interrupt_callback(ctypes.cast(None, proto), None)
+        _INTERRUPT_CB = None
+        return
+    _INTERRUPT_CB = proto(lambda _ctx: 1 if fn() else 0)  # keep the thunk alive
+    lib.faiss_b200_set_interrupt_callback(_INTERRUPT_CB, None)
 
 
 class GpuIndexFlat(Index):
@@ -416,9 +452,18 @@ class GpuIndexIVF(Index):
 class GpuIndexIVFFlat(GpuIndexIVF):
     """faiss::gpu::GpuIndexIVFFlat (faiss/gpu/GpuIndexIVFFlat.h:24-119)."""
 
-    def __init__(self, res, d, nlist, metric=METRIC_L2, device=0):
+    def __init__(self, res, d, nlist, metric=METRIC_L2, device=0, quantizer=None):
+        """quantizer: a GpuIndexFlat to share as the coarse quantiser (faiss/gpu/GpuIndexIVFFlat.h:48-59), or None"""
         super().__init__()
         self._keep.append(res)
+        if quantizer is not None:
+            self._keep.append(quantizer)
+            check(
+                lib.faiss_GpuIndexIVFFlat_new_with_quantizer(
+                    ctypes.byref(self._h), res._h, quantizer._h, int(d), ctypes.c_int64(nlist), int(metric), int(device)
+                )
+            )
+            return
         check(
             lib.faiss_GpuIndexIVFFlat_new(
                 ctypes.byref(self._h), res._h, int(d), ctypes.c_int64(nlist), int(metric), int(device)
@@ -432,10 +477,20 @@ class GpuIndexIVFFlat(GpuIndexIVF):
 class GpuIndexIVFPQ(GpuIndexIVF):
     """faiss::gpu::GpuIndexIVFPQ (faiss/gpu/GpuIndexIVFPQ.h:56-181)."""
 
-    def __init__(self, res, d, nlist, M, nbits=8, metric=METRIC_L2, device=0):
+    def __init__(self, res, d, nlist, M, nbits=8, metric=METRIC_L2, device=0, quantizer=None):
+        """quantizer: a GpuIndexFlat to share as the coarse quantiser (faiss/gpu/GpuIndexIVFPQ.h:69-82), or None"""
         super().__init__()
         self._keep.append(res)
         self.M = int(M)
+        if quantizer is not None:
+            self._keep.append(quantizer)
+            check(
+                lib.faiss_GpuIndexIVFPQ_new_with_quantizer(
+                    ctypes.byref(self._h), res._h, quantizer._h, int(d), ctypes.c_int64(nlist), ctypes.c_int64(M), ctypes.c_int64(nbits),
+                    int(metric), int(device),
+                )
+            )
+            return
         check(
             lib.faiss_GpuIndexIVFPQ_new(
                 ctypes.byref(self._h),

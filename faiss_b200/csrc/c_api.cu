@@ -528,6 +528,85 @@ void faiss_IndexShards_set_successive_ids(FaissIndexShards* p, int v) {
         s->successive_ids = v != 0;
 }
 
+// ---------------------------------------------------------------- search parameters, interrupt, shared quantiser
+struct FaissSearchParameters_H {
+    SearchParameters* p;
+};
+int faiss_SearchParametersIVF_new_with(FaissSearchParametersIVF** out, size_t nprobe, size_t max_codes) {
+    try {
+        auto* sp = new SearchParametersIVF();
+        sp->nprobe = nprobe;
+        sp->max_codes = max_codes;
+        *out = new FaissSearchParameters_H{sp};
+    }
+    CATCH_AND_HANDLE
+}
+void faiss_SearchParameters_free(FaissSearchParameters* p) {
+    if (p) {
+        delete p->p;
+        delete p;
+    }
+}
+int faiss_Index_search_with_params(
+        const FaissIndex* p, idx_t n, const float* x, idx_t k, const FaissSearchParameters* params, float* D, idx_t* I) {
+    try {
+        Index* ix = IX(p);
+        if (!params || !params->p) {
+            ix->search(n, x, k, D, I);
+        } else if (auto* g = dynamic_cast<GpuIndex*>(ix)) {
+            g->search(n, x, k, D, I, params->p);
+        } else {
+            FB_THROW_MSG("search parameters are only supported on GPU indexes");
+        }
+    }
+    CATCH_AND_HANDLE
+}
+void faiss_b200_set_interrupt_callback(int (*want_interrupt)(void*), void* ctx) {
+    InterruptCallback::set(want_interrupt, ctx);
+}
+int faiss_GpuIndexIVFFlat_new_with_quantizer(
+        FaissGpuIndex** p, FaissStandardGpuResources* r, FaissGpuIndex* coarse, int d, idx_t nlist, FaissMetricType metric, int device) {
+    try {
+        auto res = RES(r);
+        GpuIndexIVFConfig cfg;
+        cfg.device = device;
+        auto* h = new FaissIndex_H{nullptr, res};
+        try {
+            h->index = new GpuIndexIVFFlat(res, AS<GpuIndexFlat>(coarse, "GpuIndexFlat"), d, nlist, MT(metric), cfg);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndexIVFPQ_new_with_quantizer(
+        FaissGpuIndex** p,
+        FaissStandardGpuResources* r,
+        FaissGpuIndex* coarse,
+        int d,
+        idx_t nlist,
+        idx_t M,
+        idx_t nbits,
+        FaissMetricType metric,
+        int device) {
+    try {
+        auto res = RES(r);
+        GpuIndexIVFPQConfig cfg;
+        cfg.device = device;
+        auto* h = new FaissIndex_H{nullptr, res};
+        try {
+            h->index = new GpuIndexIVFPQ(res, AS<GpuIndexFlat>(coarse, "GpuIndexFlat"), d, nlist, M, nbits, MT(metric), cfg);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+
 // ---------------------------------------------------------------- NCCL communicator ownership + sharded search
 int faiss_b200_nccl_unique_id(char* out128) {
     try {
@@ -878,6 +957,130 @@ int b200_flat_tc_scores_debug(
         auto res = RES(r);
         DeviceScope s(device);
         runFlatTcScoresDebug((const __half*)Q16, nq, (const __half*)Y16, N, dpad, S, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+// ---- the remaining tier-2 seams of SURVEY 8(b): the reference's internal run* launchers on raw device buffers
+int b200_ivf_coarse(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* centroids,
+        idx_t nlist,
+        int d,
+        const float* Q,
+        idx_t nq,
+        int nprobe,
+        FaissMetricType metric,
+        float* coarse_dis,
+        idx_t* coarse_ids) {
+    try {
+        // IVFBase::searchCoarseQuantizer_ (faiss/gpu/impl/IVFBase.cu:509-545) = a Flat search with k = nprobe
+        auto res = RES(r);
+        DeviceScope s(device);
+        FB_THROW_IF_NOT(nprobe >= 1 && nprobe <= kMaxNprobe);
+        runFlatExact(res.get(), device, Q, nq, centroids, nlist, d, nprobe, MT(metric), 0, coarse_dis, coarse_ids, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_kmeans_assign(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* centroids,
+        idx_t k,
+        int d,
+        const float* x,
+        idx_t n,
+        FaissMetricType metric,
+        float* dis,
+        idx_t* assign) {
+    try {
+        // Clustering's index.search(n, x, 1) (faiss/Clustering.cpp:270-290) on raw device buffers, exact SIMT arithmetic
+        auto res = RES(r);
+        DeviceScope s(device);
+        runFlatArgmin(res.get(), device, x, n, centroids, k, d, MT(metric), dis, assign, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_ivfflat_scan(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* Q,
+        idx_t nq,
+        int d,
+        const idx_t* probes,
+        int nprobe,
+        const int64_t* list_start,
+        const int* list_len,
+        const float* arena_vecs,
+        const idx_t* arena_ids,
+        idx_t arena_elems,
+        int k,
+        FaissMetricType metric,
+        float* D,
+        idx_t* I) {
+    try {
+        // runIVFInterleavedScan (faiss/gpu/impl/IVFInterleaved.cu:179): lists = row-major fp32 runs of one arena
+        auto res = RES(r);
+        DeviceScope s(device);
+        FB_THROW_IF_NOT(k >= 1 && k <= kMaxK && nprobe >= 1 && nprobe <= kMaxNprobe);
+        runIvfFlatScan(res.get(), device, Q, nq, d, probes, nprobe, list_start, list_len, arena_vecs, arena_ids, arena_elems, k, MT(metric), D, I, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_ivfpq_scan(
+        FaissStandardGpuResources* r,
+        int device,
+        const float* Q,
+        idx_t nq,
+        int d,
+        const idx_t* probes,
+        const float* coarse_dis,
+        int nprobe,
+        const float* coarse_centroids,
+        const float* pq_centroids,
+        int M,
+        const int64_t* list_start,
+        const int* list_len,
+        const uint8_t* arena_codes,
+        const idx_t* arena_ids,
+        int k,
+        FaissMetricType metric,
+        float* D,
+        idx_t* I) {
+    try {
+        // runPQScanMultiPassNoPrecomputed (faiss/gpu/impl/PQScanMultiPassNoPrecomputed-inl.cuh:527) over vector-major
+        // [len][M] codes (the CPU ArrayInvertedLists bytes); pq_centroids [M][256][d/M]
+        auto res = RES(r);
+        DeviceScope s(device);
+        FB_THROW_IF_NOT(k >= 1 && k <= kMaxK && nprobe >= 1 && nprobe <= kMaxNprobe);
+        runIvfPqScan(res.get(), device, Q, nq, d, probes, coarse_dis, nprobe, coarse_centroids, pq_centroids, M, list_start, list_len, arena_codes, arena_ids, k, MT(metric), D, I, res->getDefaultStream(device));
+    }
+    CATCH_AND_HANDLE
+}
+int b200_ivf_append(
+        FaissStandardGpuResources* r,
+        int device,
+        const uint8_t* rows,
+        const idx_t* ids,
+        const idx_t* assign,
+        idx_t n,
+        int code_size,
+        idx_t nlist,
+        const int64_t* list_start,
+        int* list_len,
+        uint8_t* arena_codes,
+        idx_t* arena_ids) {
+    try {
+        // device-side append bookkeeping (role of IVFBase::addVectorsToLists_ + runIVFAppend, faiss/gpu/impl/IVFBase.cu:693-905,
+        // IVFAppend.cu:265): stable offsets inside each list, scatter, list lengths advanced; capacity is the caller's
+        auto res = RES(r);
+        DeviceScope s(device);
+        cudaStream_t stream = res->getDefaultStream(device);
+        auto offsets = res->temp(device, sizeof(int) * std::max<idx_t>(n, 1));
+        runIvfAppendOffsets(assign, n, nlist, list_len, offsets.as<int>(), nullptr, stream);
+        runIvfScatter(rows, ids, assign, offsets.as<int>(), n, code_size, list_start, arena_codes, arena_ids, stream);
+        runIvfCountAssign(assign, n, nlist, list_len, stream);
+        CUDA_VERIFY(cudaStreamSynchronize(stream));
     }
     CATCH_AND_HANDLE
 }

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <future>
+#include <mutex>
 #include <numeric>
 #include <random>
 #include <thread>
@@ -209,6 +210,7 @@ void GpuIndex::add_with_ids(idx_t n, const float* x, const idx_t* ids) {
     // page large adds (faiss/gpu/GpuIndex.cu:36-44,181-230): <= 512 Ki vectors and <= 256 MiB
     const idx_t maxVecs = std::max<idx_t>(1, std::min<idx_t>(idx_t(512) * 1024, (idx_t(256) << 20) / (sizeof(float) * d)));
     for (idx_t i0 = 0; i0 < n; i0 += maxVecs) {
+        InterruptCallback::check(); // between add pages
         const idx_t nb = std::min(maxVecs, n - i0);
         DeviceView<float> xv(resources_.get(), config_.device, x + (size_t)i0 * d, (size_t)nb * d, stream);
         GpuMemoryReservation genIds;
@@ -237,6 +239,43 @@ void GpuIndex::assign(idx_t n, const float* x, idx_t* labels, idx_t k) const {
     search(n, x, k, dis.as<float>(), labels);
 }
 
+// ------------------------------------------------------------------------------------------
+// InterruptCallback
+// ------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_intMu;
+InterruptCallback::Fn g_intFn = nullptr;
+void* g_intCtx = nullptr;
+} // namespace
+void InterruptCallback::set(Fn fn, void* ctx) {
+    std::lock_guard<std::mutex> g(g_intMu);
+    g_intFn = fn;
+    g_intCtx = ctx;
+}
+void InterruptCallback::clear() {
+    set(nullptr, nullptr);
+}
+bool InterruptCallback::is_interrupted() {
+    std::lock_guard<std::mutex> g(g_intMu);
+    return g_intFn != nullptr && g_intFn(g_intCtx) != 0;
+}
+void InterruptCallback::check() {
+    if (is_interrupted())
+        FB_THROW_MSG("computation interrupted");
+}
+
+void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, const SearchParameters* params) const {
+    FB_THROW_IF_NOT_MSG(!params || params->sel == nullptr, "GPU index does not support IDSelector search parameters");
+    struct Guard {
+        const SearchParameters*& slot;
+        ~Guard() {
+            slot = nullptr;
+        }
+    } guard{callParams_};
+    callParams_ = params;
+    search(n, x, k, distances, labels);
+}
+
 void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const {
     DeviceScope scope(config_.device);
     FB_THROW_IF_NOT_MSG(this->is_trained, "Index not trained");
@@ -258,6 +297,7 @@ void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t*
     maxQ = std::min<idx_t>(maxQ, (idx_t)((size_t(1) << 30) / ((size_t)k * 12 * 8)));
     maxQ = std::max<idx_t>(maxQ, 1);
     for (idx_t i0 = 0; i0 < n; i0 += maxQ) {
+        InterruptCallback::check(); // between query pages
         const idx_t nb = std::min(maxQ, n - i0);
         DeviceView<float> xv(resources_.get(), config_.device, x + (size_t)i0 * d, (size_t)nb * d, stream);
         DeviceOut<float> dv(resources_.get(), config_.device, distances + (size_t)i0 * k, (size_t)nb * k);
@@ -669,6 +709,7 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
             if (update_index)
                 index.train(k, cDev.as<float>());
             index.add(k, cDev.as<float>());
+            InterruptCallback::check(); // faiss/Clustering.cpp:356
             // early stop when the objective did not change (early_stop_threshold = 0, faiss/Clustering.cpp:360-377)
             if (it > 0) {
                 const float prev = iteration_stats[iteration_stats.size() - 2].obj;
@@ -1084,6 +1125,24 @@ GpuIndexIVF::GpuIndexIVF(
     lists_.reset(new IvfLists(resources_.get(), config.device, nlist, codeSize, pqInterleaved));
 }
 
+// the constructors taking `Index* coarseQuantizer` (faiss/gpu/GpuIndexIVFFlat.h:48-59, GpuIndexIVFPQ.h:69-82,
+// GpuIndexIVF.cu:84-100): the quantiser is shared, not owned; the index is trained iff the quantiser already
+// holds nlist centroids (the PQ of a GpuIndexIVFPQ still needs train()).  Only this library's GpuIndexFlat is
+// accepted (a CPU quantiser would put a host search on the path: allowCpuCoarseQuantizer stays unsupported).
+void GpuIndexIVF::setQuantizer(GpuIndexFlat* coarse) {
+    FB_THROW_IF_NOT_MSG(coarse != nullptr, "null coarse quantizer");
+    FB_THROW_IF_NOT_MSG(coarse->d == d, "coarse quantizer dimension mismatch");
+    FB_THROW_IF_NOT_MSG(coarse->metric_type == metric_type, "coarse quantizer metric mismatch");
+    FB_THROW_IF_NOT_MSG(coarse->getDevice() == config_.device, "coarse quantizer lives on another device");
+    FB_THROW_IF_NOT_MSG(this->ntotal == 0, "cannot swap the quantizer of a populated index");
+    if (own_fields)
+        delete quantizer;
+    quantizer = coarse;
+    own_fields = false;
+    coarseEpoch++;
+    this->is_trained = quantizer->is_trained && quantizer->ntotal == nlist && quantizerOnlyTraining_();
+}
+
 GpuIndexIVF::~GpuIndexIVF() {
     lists_.reset();
     if (own_fields)
@@ -1170,12 +1229,21 @@ void GpuIndexIVF::trainQuantizer_(idx_t n, const float* xDev) {
 }
 
 void GpuIndexIVF::searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const {
-    validateNProbe(nprobe);
+    // per-call SearchParametersIVF override the index fields (faiss/gpu/GpuIndexIVF.cu:383-406)
+    size_t use_nprobe = nprobe, use_max_codes = max_codes;
+    if (callParams_) {
+        auto* ivfParams = dynamic_cast<const SearchParametersIVF*>(callParams_);
+        FB_THROW_IF_NOT_MSG(ivfParams != nullptr, "IVF search: search parameters must be SearchParametersIVF");
+        use_nprobe = ivfParams->nprobe;
+        use_max_codes = ivfParams->max_codes;
+        FB_THROW_IF_NOT_MSG(ivfParams->quantizer_params == nullptr, "quantizer search parameters are not supported on the GPU path");
+    }
+    validateNProbe(use_nprobe);
     FB_THROW_IF_NOT_FMT(
-            max_codes == 0,
+            use_max_codes == 0,
             "GPU IVF index does not currently support max_codes (passed %zu, must be 0)",
-            max_codes);
-    const int np = (int)std::min<size_t>(nprobe, (size_t)nlist);
+            use_max_codes);
+    const int np = (int)std::min<size_t>(use_nprobe, (size_t)nlist);
     auto cD = resources_->temp(config_.device, sizeof(float) * n * np);
     auto cI = resources_->temp(config_.device, sizeof(idx_t) * n * np);
     // coarse quantisation = a Flat search with k = nprobe over the centroids (IVFBase.cu:509-545)
@@ -1220,6 +1288,17 @@ GpuIndexIVFFlat::GpuIndexIVFFlat(
         MetricType metric,
         GpuIndexIVFConfig config)
         : GpuIndexIVF(std::move(resources), dims, metric, nlist, (int)(sizeof(float) * dims), config) {}
+
+GpuIndexIVFFlat::GpuIndexIVFFlat(
+        std::shared_ptr<GpuResources> resources,
+        GpuIndexFlat* coarseQuantizer,
+        int dims,
+        idx_t nlist,
+        MetricType metric,
+        GpuIndexIVFConfig config)
+        : GpuIndexIVFFlat(std::move(resources), dims, nlist, metric, config) {
+    setQuantizer(coarseQuantizer);
+}
 
 void GpuIndexIVFFlat::train(idx_t n, const float* x) {
     DeviceScope scope(config_.device);
@@ -1294,6 +1373,19 @@ GpuIndexIVFPQ::GpuIndexIVFPQ(
             sizeof(float) * subQuantizers * 256 <= 160 * 1024,
             "Number of sub-quantizers %d: lookup table does not fit shared memory",
             (int)subQuantizers);
+}
+
+GpuIndexIVFPQ::GpuIndexIVFPQ(
+        std::shared_ptr<GpuResources> resources,
+        GpuIndexFlat* coarseQuantizer,
+        int dims,
+        idx_t nlist,
+        idx_t subQuantizers,
+        idx_t bitsPerCode,
+        MetricType metric,
+        GpuIndexIVFPQConfig config)
+        : GpuIndexIVFPQ(std::move(resources), dims, nlist, subQuantizers, bitsPerCode, metric, config) {
+    setQuantizer(coarseQuantizer);
 }
 
 GpuIndexIVFPQ::~GpuIndexIVFPQ() {}

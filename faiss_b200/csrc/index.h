@@ -119,6 +119,30 @@ struct Index {
     virtual void compute_residual_n(idx_t n, const float* xs, float* residuals, const idx_t* keys) const;
 };
 
+// faiss::SearchParameters / SearchParametersIVF (faiss/Index.h:88-93, faiss/IndexIVF.h:68-90): per-call overrides.
+// GPU indexes accept them like the reference's (faiss/gpu/GpuIndexIVF.cu:383-406): no IDSelector, max_codes == 0.
+struct SearchParameters {
+    void* sel = nullptr; // IDSelector: not supported on the GPU path (must stay null, as upstream)
+    virtual ~SearchParameters() {}
+};
+struct SearchParametersIVF : SearchParameters {
+    size_t nprobe = 1;
+    size_t max_codes = 0;
+    SearchParameters* quantizer_params = nullptr;
+};
+
+// faiss::InterruptCallback (faiss/impl/AuxIndexStructures.h): a process-wide hook polled between query pages,
+// add pages, search rounds and clustering iterations (the reference polls between tiles,
+// faiss/gpu/impl/Distance.cu:245,266,403-405); when it returns true the running call throws
+// "computation interrupted".
+struct InterruptCallback {
+    typedef int (*Fn)(void* ctx);
+    static void set(Fn fn, void* ctx);
+    static void clear();
+    static bool is_interrupted();
+    static void check(); // throws FaissException if the callback asks to stop
+};
+
 // ------------------------------------------------------------------------------------------
 // GpuIndex
 // ------------------------------------------------------------------------------------------
@@ -148,11 +172,15 @@ class GpuIndex : public Index {
     void add(idx_t n, const float* x) override;
     void add_with_ids(idx_t n, const float* x, const idx_t* ids) override;
     void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const override;
+    // faiss::Index::search(..., const SearchParameters* params) (faiss/Index.h:207-214, faiss/gpu/GpuIndex.cu:373-448)
+    void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, const SearchParameters* params) const;
     void assign(idx_t n, const float* x, idx_t* labels, idx_t k = 1) const override;
     void compute_residual(const float* x, float* residual, idx_t key) const override;
     void compute_residual_n(idx_t n, const float* xs, float* residuals, const idx_t* keys) const override;
 
    protected:
+    // the per-call parameters of the search in flight (an index instance is not re-entrant, as upstream)
+    mutable const SearchParameters* callParams_ = nullptr;
     virtual bool addImplRequiresIDs_() const = 0;
     virtual void addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) = 0;
     virtual void searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const = 0;
@@ -438,6 +466,8 @@ class GpuIndexIVF : public GpuIndex {
     void setListSizes(const idx_t* lens);
     size_t reclaimMemory();
     void reset() override;
+    // share an existing coarse quantiser instead of the internally created one (not owned)
+    void setQuantizer(GpuIndexFlat* coarse);
     // install coarse centroids [nlist,d] (copyFrom of the CPU quantizer's xb)
     void setCoarseCentroids(const float* centroidsHostOrDev);
     void getCoarseCentroids(float* out) const;
@@ -459,6 +489,10 @@ class GpuIndexIVF : public GpuIndex {
         return true;
     }
     void trainQuantizer_(idx_t n, const float* xDev);
+    // is a trained coarse quantiser all the training this index needs? (IVF-Flat: yes; IVF-PQ: the PQ too)
+    virtual bool quantizerOnlyTraining_() const {
+        return true;
+    }
     void searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const override;
     virtual void scanImpl_(
             idx_t n,
@@ -482,6 +516,14 @@ class GpuIndexIVFFlat : public GpuIndexIVF {
             idx_t nlist,
             MetricType metric = METRIC_L2,
             GpuIndexIVFConfig config = GpuIndexIVFConfig());
+    // faiss/gpu/GpuIndexIVFFlat.h:48-59: with an external (shared) coarse quantiser
+    GpuIndexIVFFlat(
+            std::shared_ptr<GpuResources> resources,
+            GpuIndexFlat* coarseQuantizer,
+            int dims,
+            idx_t nlist,
+            MetricType metric = METRIC_L2,
+            GpuIndexIVFConfig config = GpuIndexIVFConfig());
     void train(idx_t n, const float* x) override;
 
    protected:
@@ -500,6 +542,16 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
    public:
     GpuIndexIVFPQ(
             std::shared_ptr<GpuResources> resources,
+            int dims,
+            idx_t nlist,
+            idx_t subQuantizers,
+            idx_t bitsPerCode,
+            MetricType metric = METRIC_L2,
+            GpuIndexIVFPQConfig config = GpuIndexIVFPQConfig());
+    // faiss/gpu/GpuIndexIVFPQ.h:69-82: with an external (shared) coarse quantiser
+    GpuIndexIVFPQ(
+            std::shared_ptr<GpuResources> resources,
+            GpuIndexFlat* coarseQuantizer,
             int dims,
             idx_t nlist,
             idx_t subQuantizers,
@@ -538,6 +590,9 @@ class GpuIndexIVFPQ : public GpuIndexIVF {
     void getPQCentroids(float* out) const;
 
    protected:
+    bool quantizerOnlyTraining_() const override {
+        return false;
+    }
     void trainResidualQuantizer_(idx_t n, const float* xDev);
     void addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) override;
     void scanImpl_(idx_t, const float*, const idx_t*, const float*, int, int, float*, idx_t*) const override;

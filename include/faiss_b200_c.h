@@ -150,6 +150,23 @@ FB200_API void faiss_IndexShards_set_own_indices(FaissIndexShards* index, int v)
 FB200_API int faiss_IndexShards_successive_ids(const FaissIndexShards* index);
 FB200_API void faiss_IndexShards_set_successive_ids(FaissIndexShards* index, int v);
 
+/* ---- SearchParameters (faiss/Index.h:88-93, faiss/IndexIVF.h:68-90; c_api/IndexIVF_c.h faiss_SearchParametersIVF_new_with),
+   InterruptCallback (faiss/impl/AuxIndexStructures.h), constructors sharing a coarse quantiser
+   (faiss/gpu/GpuIndexIVFFlat.h:48-59, GpuIndexIVFPQ.h:69-82) ---- */
+typedef struct FaissSearchParameters_H FaissSearchParameters;
+typedef struct FaissSearchParameters_H FaissSearchParametersIVF;
+FB200_API int faiss_SearchParametersIVF_new_with(FaissSearchParametersIVF** p_sp, size_t nprobe, size_t max_codes);
+FB200_API void faiss_SearchParameters_free(FaissSearchParameters* sp);
+/* c_api/Index_c.h faiss_Index_search_with_params: per-call nprobe for IVF indexes (max_codes must be 0, no IDSelector) */
+FB200_API int faiss_Index_search_with_params(const FaissIndex* index, idx_t n, const float* x, idx_t k, const FaissSearchParameters* params, float* distances, idx_t* labels);
+/* polled between query pages, add pages and clustering iterations; non-zero return -> the running call fails with
+   "computation interrupted" (-2).  NULL clears it. */
+FB200_API void faiss_b200_set_interrupt_callback(int (*want_interrupt)(void* ctx), void* ctx);
+/* `coarse` = a GpuIndexFlat of this library on the same device (shared, not owned); the index is trained iff it
+   already holds nlist centroids (an IVFPQ still needs train() for its PQ) */
+FB200_API int faiss_GpuIndexIVFFlat_new_with_quantizer(FaissGpuIndex** p_index, FaissStandardGpuResources* res, FaissGpuIndex* coarse, int d, idx_t nlist, FaissMetricType metric, int device);
+FB200_API int faiss_GpuIndexIVFPQ_new_with_quantizer(FaissGpuIndex** p_index, FaissStandardGpuResources* res, FaissGpuIndex* coarse, int d, idx_t nlist, idx_t M, idx_t nbits, FaissMetricType metric, int device);
+
 /* ---- NCCL communicator ownership + IndexShards across ranks ----
    The reference shards over the GPUs of a box with IndexShards (one worker thread per sub-index, host heap
    merge: faiss/IndexShards.cpp:197-264, faiss/impl/ThreadedIndex-inl.h:119-194); ToGpuClonerMultiple builds it
@@ -213,6 +230,19 @@ FB200_API int b200_flat_search_exact(FaissStandardGpuResources* res, int device,
 FB200_API int b200_topk_merge(FaissStandardGpuResources* res, int device, const float* D_in, const idx_t* I_in, idx_t nq, int nshard, int k_in, const idx_t* id_offsets /* device, [nshard] or NULL */, int k, FaissMetricType metric, float* D, idx_t* I);
 /* unit-test seam for the tcgen05 path: S[nq, roundup(N,128)] = Q16 . Y16^T (fp16 inputs) */
 FB200_API int b200_flat_tc_scores_debug(FaissStandardGpuResources* res, int device, const void* Q16, idx_t nq, const void* Y16, idx_t N, int dpad, float* S);
+/* role of IVFBase::searchCoarseQuantizer_ (faiss/gpu/impl/IVFBase.cu:509-545): nprobe nearest centroids per query */
+FB200_API int b200_ivf_coarse(FaissStandardGpuResources* res, int device, const float* centroids, idx_t nlist, int d, const float* Q, idx_t nq, int nprobe, FaissMetricType metric, float* coarse_dis, idx_t* coarse_ids);
+/* role of Clustering's index.search(n, x, 1) (faiss/Clustering.cpp:270-290): nearest centroid of every point */
+FB200_API int b200_kmeans_assign(FaissStandardGpuResources* res, int device, const float* centroids, idx_t k, int d, const float* x, idx_t n, FaissMetricType metric, float* dis, idx_t* assign);
+/* role of runIVFInterleavedScan (faiss/gpu/impl/IVFInterleaved.cu:179): lists are row-major fp32 runs of one arena,
+   list l = elements [list_start[l], +list_len[l]); probes [nq, nprobe] (-1 = skip) */
+FB200_API int b200_ivfflat_scan(FaissStandardGpuResources* res, int device, const float* Q, idx_t nq, int d, const idx_t* probes, int nprobe, const int64_t* list_start, const int* list_len, const float* arena_vecs, const idx_t* arena_ids, idx_t arena_elems, int k, FaissMetricType metric, float* D, idx_t* I);
+/* role of runPQScanMultiPassNoPrecomputed + pqCodeDistances (faiss/gpu/impl/PQScanMultiPassNoPrecomputed-inl.cuh:527,
+   PQCodeDistances-inl.cuh:591) over vector-major [len][M] codes; pq_centroids [M][256][d/M] */
+FB200_API int b200_ivfpq_scan(FaissStandardGpuResources* res, int device, const float* Q, idx_t nq, int d, const idx_t* probes, const float* coarse_dis, int nprobe, const float* coarse_centroids, const float* pq_centroids, int M, const int64_t* list_start, const int* list_len, const uint8_t* arena_codes, const idx_t* arena_ids, int k, FaissMetricType metric, float* D, idx_t* I);
+/* role of IVFBase::addVectorsToLists_ + runIVFAppend (faiss/gpu/impl/IVFBase.cu:693-905, IVFAppend.cu:265): append n
+   encoded rows to their lists (stable order), list_len advanced on the device; capacity is the caller's business */
+FB200_API int b200_ivf_append(FaissStandardGpuResources* res, int device, const uint8_t* rows, const idx_t* ids, const idx_t* assign, idx_t n, int code_size, idx_t nlist, const int64_t* list_start, int* list_len, uint8_t* arena_codes, idx_t* arena_ids);
 FB200_API int b200_pq_encode(FaissStandardGpuResources* res, int device, const float* residuals, idx_t n, int d, int M, const float* pq_centroids, uint8_t* codes);
 FB200_API int b200_kmeans_update(FaissStandardGpuResources* res, int device, const float* x, const idx_t* assign, idx_t n, int d, idx_t k, float* sums, float* counts, float* centroids);
 

@@ -364,3 +364,69 @@ def test_bulk_clone_single_relayout(res, golden):
     idx.nprobe = nprobe
     D, I = idx.search(xq, k)
     o.compare_lists(golden["ivfpq_l2_D"], golden["ivfpq_l2_I"], D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+
+
+def test_search_parameters_ivf_and_shared_quantizer(res):
+    """per-call SearchParametersIVF (faiss/gpu/GpuIndexIVF.cu:383-406) and the constructors that share a coarse
+    quantiser (GpuIndexIVFFlat.h:48-59, GpuIndexIVFPQ.h:69-82)"""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(9)
+    d, nlist = 32, 32
+    xb = rs.rand(9000, d).astype(np.float32)
+    xq = rs.rand(50, d).astype(np.float32)
+    a = fb.GpuIndexIVFFlat(res, d, nlist)
+    a.setClustering(niter=5)
+    a.train(xb)
+    a.add(xb)
+    a.nprobe = 1
+    D1, I1 = a.search(xq, 10)
+    D8, I8 = a.search(xq, 10, params=fb.SearchParametersIVF(nprobe=8))
+    a.nprobe = 8
+    Dref, Iref = a.search(xq, 10)
+    assert np.array_equal(I8, Iref) and np.array_equal(D8, Dref)
+    a.nprobe = 1
+    D1b, I1b = a.search(xq, 10)
+    assert np.array_equal(I1, I1b)  # the per-call override did not stick
+    with pytest.raises(fb.FaissError):
+        a.search(xq, 10, params=fb.SearchParametersIVF(nprobe=4, max_codes=100))
+    # shared quantiser: a second IVF index over the SAME GpuIndexFlat is trained at birth and assigns identically
+    cq = fb.GpuIndexFlatL2(res, d)
+    cq.add(a.getCoarseCentroids())
+    b = fb.GpuIndexIVFFlat(res, d, nlist, quantizer=cq)
+    assert b.is_trained
+    b.add(xb)
+    b.nprobe = 8
+    Db, Ib = b.search(xq, 10)
+    assert np.array_equal(Ib, Iref) and np.array_equal(Db, Dref)
+    c = fb.GpuIndexIVFPQ(res, d, nlist, 8, 8, quantizer=cq)
+    assert not c.is_trained  # the PQ still needs training
+    c.setPQClustering(niter=4)
+    c.train(xb)
+    assert c.is_trained and np.array_equal(c.getCoarseCentroids(), a.getCoarseCentroids())
+    c.add(xb)
+    c.nprobe = 8
+    Dc, Ic = c.search(xq, 10)
+    assert (Ic >= 0).all()
+
+
+def test_interrupt_callback(res):
+    """faiss::InterruptCallback polled between pages / iterations: the call fails with 'computation interrupted'"""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(2)
+    xb = rs.rand(5000, 16).astype(np.float32)
+    idx = fb.GpuIndexFlatL2(res, 16)
+    idx.add(xb)
+    calls = []
+    fb.set_interrupt_callback(lambda: calls.append(1) or True)
+    try:
+        with pytest.raises(fb.FaissError, match="interrupted"):
+            idx.search(xb[:10], 5)
+        with pytest.raises(fb.FaissError, match="interrupted"):
+            fb.kmeans(res, xb, 8, niter=3)
+    finally:
+        fb.set_interrupt_callback(None)
+    assert calls
+    D, I = idx.search(xb[:10], 5)
+    assert (I[:, 0] == np.arange(10)).all()
