@@ -108,19 +108,28 @@ __global__ void tc_iota_kernel(int* v, int64_t n) {
         v[i] = (int)i;
 }
 
-// max bias per 256-row tile (NaN and the -inf padding never win: fmaxf drops NaN, a real row beats -inf)
+// max bias per 256-row tile (NaN and the -inf padding never win: fmaxf drops NaN, a real row beats -inf), and
+// -- at tileMax[numTiles + 1 + t] -- the MIN bias of the tile (-inf for a tile with padding rows or NaN: it then
+// simply yields no lower bound), used by the k = 1 streaming mode
 __global__ void tc_tile_max_bias_kernel(const float* __restrict__ bias, int64_t numTiles, float* __restrict__ tileMax) {
     int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= numTiles)
         return;
-    float m = -CUDART_INF_F;
-    for (int i = lane_id(); i < kTileN; i += 32)
-        m = fmaxf(m, bias[t * kTileN + i]);
+    float m = -CUDART_INF_F, mn = CUDART_INF_F;
+    for (int i = lane_id(); i < kTileN; i += 32) {
+        const float b = bias[t * kTileN + i];
+        m = fmaxf(m, b);
+        mn = (b == b) ? fminf(mn, b) : -CUDART_INF_F;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = 16; o > 0; o >>= 1) {
         m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
-    if (lane_id() == 0)
+        mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+    }
+    if (lane_id() == 0) {
         tileMax[t] = m;
+        tileMax[numTiles + 1 + t] = mn;
+    }
 }
 
 // per-batch query preparation: power-of-two scale from absmax, fp16 conversion, eps, 1/(sq*sy)
@@ -942,6 +951,7 @@ void runFlatTcSearch(
             p.invScalePtr = sc + 2;
             p.bias = bias;
             p.tileMaxBias = tileMaxBias;
+            p.tileMinBias = tileMaxBias + T + 1; // second half of the array (see tc_tile_max_bias_kernel)
             p.thr = thr.as<float>();
             p.eps = eps.as<float>();
             p.cand = arena.as<uint2>();

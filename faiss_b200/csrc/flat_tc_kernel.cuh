@@ -59,6 +59,7 @@ struct TcParams {
     const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
     const float* bias;  // [numTiles*256], -inf padded (read on the slow path only)
     const float* tileMaxBias; // [numTiles] max bias of the tile's rows (rows are stored sorted by norm)
+    const float* tileMinBias; // [numTiles] min bias of the tile's rows (SELF mode: a lower bound of the chunk's best score)
     const float* thr;   // [nq]  pass if score > thr
     const float* eps;   // [nq]  SELF mode (k = 1 streaming): a passing score v raises the thread's threshold to v - 2 eps
     uint2* cand;        // [numUnits*512][cap] (score bits, row)
@@ -92,7 +93,8 @@ __device__ __forceinline__ void epi_filter32(
         float slack, // SELF: 2 * eps of this query
         float maxb,
         uint2* buf,
-        int& cnt) {
+        int& cnt,
+        float minb = 0.f) { // SELF: min bias of the tile
     if (DUMP) {
         if (q < p.nq) {
             float* dst = p.dump + (long long)q * p.dumpLd + colBase;
@@ -111,6 +113,12 @@ __device__ __forceinline__ void epi_filter32(
         mg[g] = ptx::max3(a, c, fmaxf(__uint_as_float(r[o + 6]), __uint_as_float(r[o + 7])));
     }
     const float m = ptx::max3(mg[0], mg[1], fmaxf(mg[2], mg[3]));
+    if (SELF) {
+        // the chunk's best row scores at least fma(m, inv, min bias of the tile) (monotone rounding, bias >= minb):
+        // the running "best - 2 eps" threshold can be raised BEFORE any per-element work, so the slow path below
+        // only looks at the groups that can still hold the new best or its near-ties
+        thr = fmaxf(thr, nextafterf(fmaf(m, inv, minb) - slack, -CUDART_INF_F));
+    }
     if (fmaf(m, inv, maxb) > thr) {
         const float* bias = p.bias + colBase;
         const unsigned rowBase = (unsigned)colBase;
@@ -147,9 +155,10 @@ __device__ __forceinline__ void epi_filter64(
         float slack,
         float maxb,
         uint2* buf,
-        int& cnt) {
-    epi_filter32<DUMP, SELF>(p, r0, q, colBase, inv, thr, slack, maxb, buf, cnt);
-    epi_filter32<DUMP, SELF>(p, r1, q, colBase + 32, inv, thr, slack, maxb, buf, cnt);
+        int& cnt,
+        float minb = 0.f) {
+    epi_filter32<DUMP, SELF>(p, r0, q, colBase, inv, thr, slack, maxb, buf, cnt, minb);
+    epi_filter32<DUMP, SELF>(p, r1, q, colBase + 32, inv, thr, slack, maxb, buf, cnt, minb);
 }
 
 // SELF (k = 1 streaming mode, used for k-means assignment): one pass over all tiles, every epilogue thread keeps
@@ -316,14 +325,18 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
             // fetched one tile ahead (its L2 latency would otherwise sit on the filter's critical path)
             int t = pb < pe ? perm_tile(p, pb) : 0;
             float maxbNext = (!DUMP && pb < pe) ? __ldg(p.tileMaxBias + t) : 0.f;
+            float minbNext = (SELF && pb < pe) ? __ldg(p.tileMinBias + t) : 0.f;
             for (int pp = pb; pp < pe; pp++) {
                 const long long colBase = (long long)t * kTileN + half * kColsPerThread;
                 const float maxb = maxbNext;
+                const float minb = minbNext;
                 t += permStep;
                 if (t >= (int)p.numTiles)
                     t -= (int)p.numTiles;
                 if (!DUMP && pp + 1 < pe)
                     maxbNext = __ldg(p.tileMaxBias + t);
+                if (SELF && pp + 1 < pe)
+                    minbNext = __ldg(p.tileMinBias + t);
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {
                     const int q = h ? q1 : q0;
@@ -351,9 +364,9 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                         }
                         if (DBG == 0) {
                             if constexpr (PARTS == 2)
-                                epi_filter64<DUMP, SELF>(p, a0, a1, q, colBase + blk * 64, inv, thr, slack, maxb, buf, cnt);
+                                epi_filter64<DUMP, SELF>(p, a0, a1, q, colBase + blk * 64, inv, thr, slack, maxb, buf, cnt, minb);
                             else
-                                epi_filter32<DUMP, SELF>(p, a0, q, colBase + blk * 32, inv, thr, slack, maxb, buf, cnt);
+                                epi_filter32<DUMP, SELF>(p, a0, q, colBase + blk * 32, inv, thr, slack, maxb, buf, cnt, minb);
                         }
                     }
                     if (h) {

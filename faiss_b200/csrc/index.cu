@@ -388,7 +388,7 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
     const int64_t padRows = round_up(n, 256) + 256; // whole 256-row tiles, -inf beyond n
     y16_.resize((size_t)n * dpad_, stream);
     bias_.resize((size_t)padRows, stream);
-    tileMaxBias_.resize((size_t)(padRows / 256), stream);
+    tileMaxBias_.resize((size_t)(padRows / 256) * 2, stream); // [T+1] max bias per tile, then [T+1] min bias per tile
     const bool sorted = metric_type == METRIC_L2; // IP has no bias: row order is kept
     if (sorted)
         perm_.resize((size_t)n, stream);
