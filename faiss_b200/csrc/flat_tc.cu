@@ -33,6 +33,7 @@
 #include <cub/cub.cuh>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "comm.h"
@@ -300,6 +301,181 @@ __global__ void tc_select_kernel(
             contrib[q] = c0;
             contrib[nq + q] = -c1; // max-reduced: -min_r c1 (+inf if any shard cannot vouch for kFrac rows)
         }
+    }
+}
+
+// ---- threshold selection WITHOUT sorting (k <= 128): the round only needs (a) the k-th best approximate score seen
+// so far and (b) the set of entries above the new threshold -- not an ordered list.  One warp per query: the surviving
+// base-list entries and the round's candidates are gathered into a per-warp shared-memory array (ballot compaction),
+// their order-preserving integer keys are pulled into registers (kSelPerLane per lane), the k-th largest key is found
+// by a 32-step bitwise bisection (one compare per register and step + one warp reduction), and the entries above the
+// new threshold are written back compacted (unsorted; the exact re-rank orders them).  ~2-3 k instructions per query
+// and round instead of the ~15 k of the bitonic list maintenance, and no bank conflicts.
+constexpr int kSelCap = 1536;
+constexpr int kSelPerLane = kSelCap / 32;
+constexpr int kSelWarps = 4;
+
+__global__ void __launch_bounds__(kSelWarps * 32) tc_select_bisect_kernel(
+        int nq,
+        int k,
+        int LIST,
+        int slices,
+        int parts,
+        const uint2* __restrict__ cand,
+        int cap,
+        const int* __restrict__ candCount,
+        const float* __restrict__ eps,
+        float* __restrict__ baseKey, // [nq][LIST]  (-score), valid entries first, unsorted
+        int* __restrict__ baseId,    // [nq][LIST]
+        float* __restrict__ thr,
+        int* __restrict__ flags,
+        float* __restrict__ contrib,
+        int kFrac) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = lane_id();
+    const int q = blockIdx.x * kSelWarps + warp;
+    if (q >= nq)
+        return;
+    uint2* buf = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * kSelCap;
+    const float thrNow = thr[q];
+    const unsigned lt = (1u << lane) - 1u;
+    int E = 0;
+    int overflow = 0;
+    // (1) the base list: valid entries are packed at the front.  All LIST/32 loads are independent (no early exit)
+    // so they overlap; entries a raised threshold excludes are dropped by the final compaction, not here.
+    float* bk = baseKey + (int64_t)q * LIST;
+    int* bi = baseId + (int64_t)q * LIST;
+    {
+        constexpr int kMaxListIter = 8; // LIST <= 256
+        int ids[kMaxListIter];
+        float scs[kMaxListIter];
+#pragma unroll
+        for (int it = 0; it < kMaxListIter; it++) {
+            const int e = it * 32 + lane;
+            ids[it] = e < LIST ? bi[e] : IdLimits<int>::max();
+            scs[it] = e < LIST ? -bk[e] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < kMaxListIter; it++) {
+            const bool valid = ids[it] != IdLimits<int>::max();
+            const unsigned m = __ballot_sync(kFullMask, valid);
+            if (valid)
+                buf[E + __popc(m & lt)] = make_uint2(__float_as_uint(scs[it]), (unsigned)ids[it]);
+            E += __popc(m);
+        }
+    }
+    // (2) this round's candidates.  32 segments at a time: a warp scan of their counts gives every lane the offset
+    // of ITS segment, then the lanes copy their segments in parallel (one memory round trip per batch of 32
+    // segments instead of one per segment -- the gather is latency-bound, not bandwidth-bound).
+    const int pair = q / kPairM, prow = q % kPairM;
+    const int qPairs = (nq + kPairM - 1) / kPairM;
+    const int nseg = slices * parts;
+    for (int s0 = 0; s0 < nseg; s0 += 32) {
+        const int si = s0 + lane;
+        long long mySeg = 0;
+        int myCount = 0;
+        if (si < nseg) {
+            const int s = si / parts, h = si - s * parts;
+            mySeg = ((long long)(s * qPairs + pair) * kPairM + prow) * parts + h;
+            myCount = candCount[mySeg];
+            if (myCount > cap) {
+                overflow = 1;
+                myCount = cap;
+            }
+        }
+        int incl = myCount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        if (total == 0)
+            continue;
+        if (E + total > kSelCap) { // cannot hold more: certificate lost for this query
+            overflow = 1;
+            break;
+        }
+        const uint2* sp = cand + mySeg * cap;
+        uint2* dst = buf + E + incl - myCount;
+        for (int j = 0; j < myCount; j++)
+            dst[j] = sp[j];
+        E += total;
+    }
+    overflow = __any_sync(kFullMask, overflow) ? 1 : 0;
+    __syncwarp();
+    // (3) order-preserving keys into registers (0 sorts below every float, including -inf)
+    unsigned key[kSelPerLane];
+#pragma unroll
+    for (int i = 0; i < kSelPerLane; i++) {
+        const int idx = i * 32 + lane;
+        key[i] = idx < E ? float_to_ordered(__uint_as_float(buf[idx].x)) : 0u;
+    }
+    const int nIter = (E + 31) >> 5;
+    // k-th largest key (0 if fewer than kk entries)
+    auto kthLargest = [&](int kk) -> unsigned {
+        if (E < kk)
+            return 0u;
+        unsigned T = 0;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            const unsigned c = T | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int i = 0; i < kSelPerLane; i++)
+                if (i < nIter)
+                    cnt += key[i] >= c ? 1 : 0;
+            cnt = __reduce_add_sync(kFullMask, cnt);
+            if (cnt >= kk)
+                T = c;
+        }
+        return T;
+    };
+    const float e2 = eps[q];
+    const unsigned Tk = kthLargest(k);
+    float t = -CUDART_INF_F;
+    float kthScore = -CUDART_INF_F;
+    if (Tk != 0u) {
+        kthScore = ordered_to_float(Tk);
+        t = nextafterf(kthScore - 2.f * e2, -CUDART_INF_F);
+    }
+    const float tNew = fmaxf(t, thrNow);
+    // (4) survivors -> base list (compacted, unsorted), sentinels behind them
+    int W = 0;
+#pragma unroll 1
+    for (int i = 0; i < nIter; i++) {
+        const int idx = i * 32 + lane;
+        const uint2 v = idx < E ? buf[idx] : make_uint2(0, 0);
+        const bool keep = idx < E && __uint_as_float(v.x) > tNew;
+        const unsigned m = __ballot_sync(kFullMask, keep);
+        const int pos = W + __popc(m & lt);
+        if (keep && pos < LIST) {
+            bk[pos] = -__uint_as_float(v.x);
+            bi[pos] = (int)v.y;
+        }
+        W += __popc(m);
+    }
+    if (W > LIST) {
+        overflow = 1; // more entries above the threshold than the list holds: masses of near-ties
+        W = LIST;
+    }
+    for (int j = W + lane; j < LIST; j += 32) {
+        bk[j] = CUDART_INF_F;
+        bi[j] = IdLimits<int>::max();
+    }
+    if (contrib) {
+        const unsigned Tf = kFrac == k ? Tk : kthLargest(kFrac);
+        if (lane == 0) {
+            contrib[q] = Tk != 0u ? kthScore - e2 : -CUDART_INF_F;
+            contrib[nq + q] = Tf != 0u ? -(ordered_to_float(Tf) - e2) : CUDART_INF_F;
+        }
+    }
+    if (lane == 0) {
+        thr[q] = tNew;
+        if (overflow)
+            flags[q] = 1;
     }
 }
 
@@ -825,6 +1001,12 @@ void runFlatTcSearch(
     int r0Tiles = std::max(r0Env > 0 ? r0Env : std::max(1, (40 * k + kTileN - 1) / kTileN), (k + 127) / 128 * 2);
     if (nShards > 1) // pooled evidence: nShards * r0Tiles tiles; a shard must still be able to vouch for kFrac rows
         r0Tiles = std::max<int>((r0Tiles + nShards - 1) / nShards, std::max(2, (2 * kFrac + kTileN - 1) / kTileN));
+    // threshold selection by bisection (no sorted lists) holds kSelCap entries per query and round: the all-pass first
+    // round is sized to 3/4 of that (FB200_TC_SELECT=sort keeps the bitonic list kernel for A/B runs)
+    static const bool selSortEnv = getenv("FB200_TC_SELECT") && std::string(getenv("FB200_TC_SELECT")) == "sort";
+    const bool useBisect = LIST <= 256 && !selSortEnv;
+    if (useBisect)
+        r0Tiles = std::min(r0Tiles, std::max(2, kSelCap * 3 / 4 / kTileN));
     // queries per pass: bounds the candidate arena, whose largest user is the all-pass round 0
     // (512 KB per query pair and tile) -- 16384 queries at k = 100, up to 131072 for small k
     // k = 1 (k-means assignment, the coarse quantiser of an add): streaming mode -- one pass over all tiles with
@@ -983,22 +1165,31 @@ void runFlatTcSearch(
                 continue;
             }
             KernelTiming::begin("tc_select", stream);
-            tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
-                    (int)nq,
-                    k,
-                    LIST,
-                    r.slices,
-                    parts,
-                    arena.as<uint2>(),
-                    r.cap,
-                    counts.as<int>(),
-                    eps.as<float>(),
-                    baseKey.as<float>(),
-                    baseId.as<int>(),
-                    thr.as<float>(),
-                    flags.as<int>(),
-                    shard ? contrib.as<float>() : nullptr,
-                    kFrac);
+            if (useBisect) {
+                const size_t bsmem = sizeof(uint2) * kSelCap * kSelWarps;
+                CUDA_VERIFY(cudaFuncSetAttribute(tc_select_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+                tc_select_bisect_kernel<<<(unsigned)ceil_div(nq, kSelWarps), kSelWarps * 32, bsmem, stream>>>(
+                        (int)nq, k, LIST, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(),
+                        baseKey.as<float>(), baseId.as<int>(), thr.as<float>(), flags.as<int>(),
+                        shard ? contrib.as<float>() : nullptr, kFrac);
+            } else {
+                tc_select_kernel<<<(unsigned)ceil_div(nq, selWarps), selWarps * 32, selSmem, stream>>>(
+                        (int)nq,
+                        k,
+                        LIST,
+                        r.slices,
+                        parts,
+                        arena.as<uint2>(),
+                        r.cap,
+                        counts.as<int>(),
+                        eps.as<float>(),
+                        baseKey.as<float>(),
+                        baseId.as<int>(),
+                        thr.as<float>(),
+                        flags.as<int>(),
+                        shard ? contrib.as<float>() : nullptr,
+                        kFrac);
+            }
             KernelTiming::end("tc_select", stream);
             CUDA_CHECK_LAST();
             if (shard) {

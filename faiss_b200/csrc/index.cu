@@ -380,6 +380,16 @@ void GpuIndexFlat::addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) {
     tcDirty_ = true;
 }
 
+void GpuIndexFlat::replaceVectorsDevice(idx_t n, const float* xDev) {
+    DeviceScope scope(config_.device);
+    auto stream = stream_();
+    vecs_.resize((size_t)n * d, stream); // keeps the allocation when it is large enough
+    if (n > 0)
+        CUDA_VERIFY(cudaMemcpyAsync(vecs_.data(), xDev, sizeof(float) * n * d, cudaMemcpyDeviceToDevice, stream));
+    this->ntotal = n;
+    tcDirty_ = true;
+}
+
 void GpuIndexFlat::prepareTensorCoreData_() const {
     if (!tcDirty_)
         return;
@@ -705,10 +715,13 @@ void Clustering::train(idx_t nx, const float* x_in, GpuIndexFlat& index) {
                 fflush(stdout);
             }
             runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
-            index.reset();
-            if (update_index)
+            if (update_index) {
+                index.reset();
                 index.train(k, cDev.as<float>());
-            index.add(k, cDev.as<float>());
+                index.add(k, cDev.as<float>());
+            } else {
+                index.replaceVectorsDevice(k, cDev.as<float>());
+            }
             InterruptCallback::check(); // faiss/Clustering.cpp:356
             // early stop when the objective did not change (early_stop_threshold = 0, faiss/Clustering.cpp:360-377)
             if (it > 0) {
@@ -864,8 +877,7 @@ void Clustering::trainSharded(idx_t nLocal, const float* x_in, GpuIndexFlat& ind
             fflush(stdout);
         }
         runKmeansPostProcess(cDev.as<float>(), (int64_t)k, (int)d, spherical, int_centroids, stream);
-        index.reset();
-        index.add(k, cDev.as<float>());
+        index.replaceVectorsDevice(k, cDev.as<float>());
         if (it > 0) {
             const float prev = iteration_stats[iteration_stats.size() - 2].obj;
             if (prev != 0 && std::fabs((double)prev - (double)hobj) / std::fabs((double)prev) <= 0.0)

@@ -257,6 +257,9 @@ class GpuIndexFlat : public GpuIndex {
     void setUseTensorCores(bool v) {
         flatConfig_.useTensorCores = v;
     }
+    // replace the whole content by n device rows without giving the storage back (the k-means loop installs a new
+    // centroid table every iteration: reset() + add() would free and re-allocate five buffers each time)
+    void replaceVectorsDevice(idx_t n, const float* xDev);
     // diagnostics
     mutable int lastSearchUsedTensorCores = 0;
     mutable int lastSearchFallbackQueries = 0;

@@ -653,7 +653,7 @@ void runIvfPqScanInterleaved(
     if (nq == 0)
         return;
     FB_THROW_IF_NOT(ivfPqInterleavedSupported(M));
-    const int LIST = std::max(64, next_pow2(k));
+    const int LIST = std::max(CtaTopK<int>::BUF, next_pow2(k)); // a sorted buffer (<= BUF entries) is merged into the list
     const bool wide = arenaElems >= (int64_t(1) << 31) - 1; // arena positions need 64-bit list ids
     const int smemBase = probedSmemBase(device, stream);
     const int kScanWarps = smemBase == kExpectedSmemBase ? scanWarps() : 16;

@@ -206,6 +206,16 @@ void StandardGpuResources::initializeForDevice(int device) {
             prop.minor);
     FB_THROW_IF_NOT(prop.warpSize == 32); // faiss/gpu/StandardGpuResources.cpp:396-401
 
+    // stream-ordered scratch (cudaMallocAsync in the k-means update / debug seams): keep up to 2 GiB in the
+    // device's default pool instead of returning it to the driver at every synchronisation
+    {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = uint64_t(2) << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     PerDevice d;
     d.numSMs = prop.multiProcessorCount;
     CUDA_VERIFY(cudaStreamCreateWithFlags(&d.defaultStream, cudaStreamNonBlocking));

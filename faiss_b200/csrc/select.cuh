@@ -219,7 +219,11 @@ struct WarpTopK {
 // under a CTA-wide lock.  The result is the exact top-k by (key, id) whatever the interleaving.
 template <typename IdT>
 struct CtaTopK {
-    static constexpr int BUF = 64;
+    // a warp offers its buffer to the list once it holds more than kTrigger entries; while the list is busy (another
+    // warp merging) and the buffer still has room for one more round of 32 it simply keeps scanning -- it only
+    // blocks on the lock when the buffer could overflow
+    static constexpr int BUF = 128;
+    static constexpr int kTrigger = 32;
     SmemTopK<IdT> q; // q.keys/q.ids = shared list, q.bkeys/q.bids = this warp's buffer
     int* lock;
     volatile float* sthr;
@@ -271,7 +275,7 @@ struct CtaTopK {
                 q.bids[pos] = id;
             }
             cnt += __popc(m);
-            if (cnt > BUF - 32)
+            if (cnt > kTrigger)
                 drain();
         }
     }
@@ -279,23 +283,31 @@ struct CtaTopK {
     // drop buffered entries that no longer beat the (refreshed) threshold
     __device__ void compact() {
         const int lane = lane_id();
-        const bool h0 = lane < cnt, h1 = lane + 32 < cnt;
-        const float k0 = h0 ? q.bkeys[lane] : 0.f, k1 = h1 ? q.bkeys[lane + 32] : 0.f;
-        const IdT i0 = h0 ? q.bids[lane] : 0, i1 = h1 ? q.bids[lane + 32] : 0;
-        const bool p0 = h0 && k0 <= thr, p1 = h1 && k1 <= thr;
-        const unsigned m0 = __ballot_sync(kFullMask, p0), m1 = __ballot_sync(kFullMask, p1);
+        constexpr int S = BUF / 32;
+        float kk[S];
+        IdT ii[S];
+        bool pp[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const bool h = lane + 32 * s < cnt;
+            kk[s] = h ? q.bkeys[lane + 32 * s] : 0.f;
+            ii[s] = h ? q.bids[lane + 32 * s] : 0;
+            pp[s] = h && kk[s] <= thr;
+        }
+        __syncwarp(); // every entry is in registers before any slot is overwritten
         const unsigned lt = (1u << lane) - 1u;
-        if (p0) {
-            const int pos = __popc(m0 & lt);
-            q.bkeys[pos] = k0;
-            q.bids[pos] = i0;
+        int base = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const unsigned m = __ballot_sync(kFullMask, pp[s]);
+            if (pp[s]) {
+                const int pos = base + __popc(m & lt);
+                q.bkeys[pos] = kk[s];
+                q.bids[pos] = ii[s];
+            }
+            base += __popc(m);
         }
-        if (p1) {
-            const int pos = __popc(m0) + __popc(m1 & lt);
-            q.bkeys[pos] = k1;
-            q.bids[pos] = i1;
-        }
-        cnt = __popc(m0) + __popc(m1);
+        cnt = base;
         __syncwarp();
     }
 
@@ -306,15 +318,21 @@ struct CtaTopK {
         if (t < thr) { // somebody tightened the threshold since we filtered: re-filter first
             thr = t;
             compact();
-            if (!force && cnt <= BUF - 32)
+            if (!force && cnt <= kTrigger)
                 return;
         }
         if (cnt == 0)
             return;
+        // the list is busy and the next round of 32 still fits: come back later instead of spinning
+        if (!force && cnt <= BUF - 32 && *reinterpret_cast<volatile int*>(lock) != 0)
+            return;
         const int n = q.sort_buffer(cnt); // private: no lock needed
         if (lane_id() == 0) {
-            while (atomicCAS(lock, 0, 1) != 0)
-                __nanosleep(32);
+            unsigned ns = 32;
+            while (atomicCAS(lock, 0, 1) != 0) {
+                __nanosleep(ns);
+                ns = min(ns * 2, 512u);
+            }
         }
         __syncwarp();
         __threadfence_block();
