@@ -569,6 +569,21 @@ class IndexShards(Index):
         self._shards = []
 
 
+class IndexShardsIVF(IndexShards):
+    """faiss::IndexShardsIVF (faiss/IndexShardsIVF.cpp:100-251): IVF shards over one shared coarse quantiser (a
+    GpuIndexFlat): one coarse search, search_preassigned on every shard, merge."""
+
+    def __init__(self, quantizer, nlist, threaded=False, successive_ids=True):
+        Index.__init__(self)
+        self._keep.append(quantizer)
+        check(lib.faiss_IndexShardsIVF_new(ctypes.byref(self._h), quantizer._h, ctypes.c_int64(nlist), int(bool(threaded)), int(bool(successive_ids))))
+        self._shards = []
+
+    def add_shard(self, index):
+        check(lib.faiss_IndexShardsIVF_add_shard(self._h, index._h))
+        self._shards.append(index)
+
+
 def nccl_unique_id():
     """128 bytes to hand to every rank's StandardGpuResources.ncclInitRank (ncclGetUniqueId)."""
     buf = ctypes.create_string_buffer(128)

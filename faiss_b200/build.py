@@ -75,40 +75,8 @@ def build(jobs=None, force=False, verbose=True):
     return LIB
 
 
-def build_adapter(verbose=True):
-    """Compile the faiss::Index adapter (faiss_b200/adapter) and its test driver against the REFERENCE's headers
-    (/root/reference) and the reference CPU library (oracle/_ref).  Only possible where /root/reference exists;
-    the binary (tests/adapter/_build/adapter_test, git-ignored) travels to the GPU box with the snapshot."""
-    ref = "/root/reference"
-    root = os.path.abspath(os.path.join(HERE, ".."))
-    reflib = os.path.join(root, "oracle", "_ref", "libfaiss_ref.so")
-    if not os.path.isdir(os.path.join(ref, "faiss")) or not os.path.exists(reflib):
-        return None
-    outdir = os.path.join(root, "tests", "adapter", "_build")
-    os.makedirs(outdir, exist_ok=True)
-    out = os.path.join(outdir, "adapter_test")
-    srcs = [os.path.join(HERE, "adapter", "faiss_b200_adapter.cpp"), os.path.join(root, "tests", "adapter", "adapter_test.cpp")]
-    deps = srcs + [os.path.join(HERE, "adapter", "faiss_b200_adapter.h"), LIB, reflib, os.path.join(root, "include", "faiss_b200_c.h")]
-    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in deps):
-        return out
-    import sysconfig
-
-    blasdir = os.path.join(sysconfig.get_paths()["purelib"], "opencv_python_headless.libs")  # OpenBLAS + libgfortran of libfaiss_ref
-    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-fopenmp", "-w", "-Wl,-rpath-link," + blasdir, "-I" + ref, "-I" + os.path.join(root, "include"),
-           "-I" + os.path.join(HERE, "adapter")] + srcs + [
-        "-o", out, reflib, LIB, "-L/usr/local/cuda/lib64", "-lcudart",
-        "-Wl,-rpath,$ORIGIN/../../../oracle/_ref:$ORIGIN/../../../faiss_b200:/usr/local/cuda/lib64"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("adapter build failed:\n%s\n%s" % (r.stdout[-3000:], r.stderr[-3000:]))
-    if verbose:
-        print("[faiss_b200.build] built", out, flush=True)
-    return out
-
-
 if __name__ == "__main__":
     j = None
     if "-j" in sys.argv:
         j = int(sys.argv[sys.argv.index("-j") + 1])
     build(jobs=j, force="--force" in sys.argv)
-    build_adapter()

@@ -641,6 +641,25 @@ int faiss_StandardGpuResources_ncclRank(FaissStandardGpuResources* r, int device
     }
     CATCH_AND_HANDLE
 }
+int faiss_IndexShardsIVF_new(FaissIndexShards** p, FaissGpuIndex* quantizer, idx_t nlist, int threaded, int successive_ids) {
+    try {
+        auto* h = new FaissIndex_H();
+        try {
+            h->index = new IndexShardsIVF(AS<GpuIndexFlat>(quantizer, "GpuIndexFlat"), nlist, threaded != 0, successive_ids != 0);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_IndexShardsIVF_add_shard(FaissIndexShards* p, FaissIndex* shard) {
+    try {
+        AS<IndexShardsIVF>(p, "IndexShardsIVF")->add_shard(IX(shard));
+    }
+    CATCH_AND_HANDLE
+}
 int faiss_IndexShards_lastSearchPath(const FaissIndexShards* p) {
     try {
         return AS<IndexShards>(p, "IndexShards")->lastSearchPath;

@@ -1777,6 +1777,58 @@ void IndexShards::search(idx_t n, const float* x, idx_t k, float* distances, idx
 
 
 // ------------------------------------------------------------------------------------------
+// IndexShardsIVF
+// ------------------------------------------------------------------------------------------
+IndexShardsIVF::IndexShardsIVF(GpuIndexFlat* quantizer_, idx_t nlist_, bool threaded_, bool successive_ids_)
+        : IndexShards(quantizer_ ? quantizer_->d : 0, threaded_, successive_ids_), quantizer(quantizer_), nlist(nlist_) {
+    FB_THROW_IF_NOT_MSG(quantizer != nullptr, "null quantizer");
+    metric_type = quantizer->metric_type;
+}
+
+void IndexShardsIVF::add_shard(Index* idx) {
+    auto* ivf = dynamic_cast<GpuIndexIVF*>(idx);
+    FB_THROW_IF_NOT_MSG(ivf != nullptr, "IndexShardsIVF: shards must be IVF indexes");
+    FB_THROW_IF_NOT_MSG(ivf->nlist == nlist, "IndexShardsIVF: shard has a different nlist");
+    IndexShards::add_shard(idx);
+}
+
+void IndexShardsIVF::search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const {
+    FB_THROW_IF_NOT(k > 0);
+    const int nshard = count();
+    FB_THROW_IF_NOT_MSG(nshard > 0, "no shards");
+    lastSearchPath = 0;
+    auto* index0 = dynamic_cast<GpuIndexIVF*>(shards_[0]);
+    const idx_t nprobe = std::min<idx_t>((idx_t)index0->nprobe, nlist);
+    // ONE coarse quantisation for all shards (faiss/IndexShardsIVF.cpp:183-188)
+    std::vector<float> Dq((size_t)n * nprobe);
+    std::vector<idx_t> Iq((size_t)n * nprobe);
+    quantizer->search(n, x, nprobe, Dq.data(), Iq.data());
+    std::vector<idx_t> translations(nshard, 0);
+    if (successive_ids)
+        for (int s = 0; s + 1 < nshard; s++)
+            translations[s + 1] = translations[s] + shards_[s]->ntotal;
+    std::vector<float> all_distances((size_t)nshard * k * n);
+    std::vector<idx_t> all_labels((size_t)nshard * k * n);
+    float* ad = all_distances.data();
+    idx_t* al = all_labels.data();
+    const float* dq = Dq.data();
+    const idx_t* iq = Iq.data();
+    runOnIndex([=, &translations](int no, Index* indexIn) {
+        auto* index = dynamic_cast<GpuIndexIVF*>(indexIn);
+        FB_THROW_IF_NOT_MSG((idx_t)index->nprobe == nprobe, "inconsistent nprobe (every shard must use the same nprobe <= nlist)");
+        index->search_preassigned(n, x, k, iq, dq, ad + (size_t)no * k * n, al + (size_t)no * k * n);
+        const idx_t tr = translations[no];
+        if (tr != 0) {
+            idx_t* l = al + (size_t)no * k * n;
+            for (idx_t i = 0; i < n * k; i++)
+                if (l[i] >= 0)
+                    l[i] += tr;
+        }
+    });
+    merge_knn_results_host(n, k, nshard, metric_type, ad, al, distances, labels);
+}
+
+// ------------------------------------------------------------------------------------------
 // DistributedIndexShards
 // ------------------------------------------------------------------------------------------
 DistributedIndexShards::DistributedIndexShards(std::shared_ptr<GpuResources> resources, GpuIndex* local, bool successive)

@@ -643,7 +643,7 @@ class IndexShards : public Index {
     // which path the last search took: 0 = thread-per-shard + host merge (the reference's), 1 = NCCL fast path
     mutable int lastSearchPath = 0;
 
-   private:
+   protected:
     template <typename F>
     void runOnIndex(F f) const;
     // fast path: every shard is a GpuIndex on its own device and the shards' resources hold one NCCL clique
@@ -651,6 +651,18 @@ class IndexShards : public Index {
     bool ncclFastPath_(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const;
     std::vector<Index*> shards_;
     mutable std::vector<std::unique_ptr<DistributedIndexShards>> dist_; // one per device, built on first use
+};
+
+// faiss::IndexShardsIVF (faiss/IndexShardsIVF.h, IndexShardsIVF.cpp:100-251): shards are IVF indexes over ONE common
+// coarse quantiser (GpuMultipleClonerOptions::common_ivf_quantizer, faiss/gpu/GpuCloner.cpp:418-436): the coarse search
+// runs once, every shard scans its part of the probed lists through search_preassigned, results are merged.
+class IndexShardsIVF : public IndexShards {
+   public:
+    IndexShardsIVF(GpuIndexFlat* quantizer, idx_t nlist, bool threaded = false, bool successive_ids = true);
+    GpuIndexFlat* quantizer; // shared, not owned
+    idx_t nlist;
+    void add_shard(Index* idx); // must be a GpuIndexIVF with the same nlist
+    void search(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels) const override;
 };
 
 // ------------------------------------------------------------------------------------------

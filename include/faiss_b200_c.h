@@ -183,6 +183,11 @@ FB200_API int faiss_b200_nccl_unique_id(char* out128);
 FB200_API int faiss_StandardGpuResources_ncclInitRank(FaissStandardGpuResources* res, int device, int nranks, int rank, const char* unique_id128);
 FB200_API int faiss_StandardGpuResources_ncclInitAll(FaissStandardGpuResources* res, int ndev, const int* devices);
 FB200_API int faiss_StandardGpuResources_ncclRank(FaissStandardGpuResources* res, int device, int* rank, int* nranks);
+/* faiss::IndexShardsIVF (faiss/IndexShardsIVF.cpp:100-251; GpuMultipleClonerOptions::common_ivf_quantizer,
+   faiss/gpu/GpuCloner.cpp:418-436): IVF shards over ONE shared coarse quantiser -- the coarse search runs once, every
+   shard scans through search_preassigned, results are merged.  `quantizer` = a GpuIndexFlat (shared, not owned). */
+FB200_API int faiss_IndexShardsIVF_new(FaissIndexShards** p_index, FaissGpuIndex* quantizer, idx_t nlist, int threaded, int successive_ids);
+FB200_API int faiss_IndexShardsIVF_add_shard(FaissIndexShards* index, FaissIndex* shard);
 /* path of the last faiss_Index_search on an IndexShards: 0 = thread per shard + host merge, 1 = NCCL fast path */
 FB200_API int faiss_IndexShards_lastSearchPath(const FaissIndexShards* index);
 FB200_API int faiss_DistributedIndexShards_new(FaissIndexShards** p_index, FaissStandardGpuResources* res, FaissGpuIndex* local_shard, int successive_ids);

@@ -16,9 +16,9 @@ def test_adapter_compiles_against_reference_headers():
         if not os.path.exists(BIN):
             pytest.skip("the reference tree is not mounted here and no prebuilt adapter binary travelled")
         return
-    from faiss_b200 import build as b
+    from tests.adapter.build_adapter import build_adapter
 
-    out = b.build_adapter(verbose=False)
+    out = build_adapter(verbose=False)
     assert out and os.path.exists(out)
     syms = subprocess.run(["nm", "-C", out], capture_output=True, text=True).stdout
     for cls in ("B200IndexFlat", "B200IndexIVFPQ", "index_cpu_to_b200", "index_b200_to_cpu"):

@@ -430,3 +430,31 @@ def test_interrupt_callback(res):
     assert calls
     D, I = idx.search(xb[:10], 5)
     assert (I[:, 0] == np.arange(10)).all()
+
+
+def test_index_shards_ivf_common_quantizer(res, golden):
+    """faiss::IndexShardsIVF / common_ivf_quantizer (faiss/IndexShardsIVF.cpp:163-251): the shards share ONE coarse
+    quantiser, which is searched once; the merged result equals the unsharded index"""
+    import faiss_b200 as fb
+    from faiss_b200 import cloner
+
+    N, d, nlist, M, nq, k, nprobe = [int(v) for v in golden["ivfpq_shape"]]
+    codes, ids = _lists_from_golden(golden, "l2", M)
+    xq = o.float_rand(nq * d, 22).reshape(nq, d)
+    cq = fb.GpuIndexFlatL2(res, d)
+    cq.add(golden["ivfpq_l2_centroids"])
+    parts = cloner.shard_ivf_lists(codes, ids, M, 3, cloner.SHARD_BY_ID_MOD)
+    shards = fb.IndexShardsIVF(cq, nlist, threaded=True, successive_ids=False)
+    for ci, ii in parts:
+        sub = fb.GpuIndexIVFPQ(res, d, nlist, M, 8, fb.METRIC_L2, quantizer=cq)
+        sub.setPQCentroids(golden["ivfpq_l2_pq"])
+        sub.setListSizes(np.array([len(a) for a in ii], dtype=np.int64))
+        for l in range(nlist):
+            if len(ii[l]):
+                sub.setList(l, ci[l], ii[l])
+        sub.setIsTrained(True)
+        sub.nprobe = nprobe
+        shards.add_shard(sub)
+    assert shards.ntotal == N
+    D, I = shards.search(xq, k)
+    o.compare_lists(golden["ivfpq_l2_D"], golden["ivfpq_l2_I"], D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
