@@ -9,7 +9,7 @@
 // lists are moved in the CPU ArrayInvertedLists byte format, so copyTo(copyFrom(x)) is byte-identical).
 //
 // Compiled against the reference's headers only (no reference source is copied); built by
-// faiss_b200/build.py:build_adapter() where /root/reference is available and exercised by tests/adapter/.
+// tests/adapter/build_adapter.py where /root/reference is available and exercised by tests/adapter/.
 #pragma once
 
 #include <faiss/Index.h>
