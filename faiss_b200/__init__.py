@@ -658,6 +658,27 @@ def kmeans_ex(res, x, k, niter=25, seed=1234, max_points_per_centroid=256, metri
     return cent, obj
 
 
+def bfKnn(res, xq, xb, k, metric=METRIC_L2, device=0):
+    """faiss.knn_gpu / bfKnn (faiss/gpu/GpuDistance.h:33-181, faiss/python/gpu_wrappers.py:60-200): brute-force
+    k-NN of xq in xb, row-major fp32, numpy or torch CUDA inputs; outputs follow xq's residency."""
+    xq, xb = _as_f32(xq), _as_f32(xb)
+    nq, d = xq.shape
+    assert xb.shape[1] == d
+    D = _empty_like_residency(xq, (nq, k), np.float32)
+    I = _empty_like_residency(xq, (nq, k), np.int64)
+    if _is_torch(xq) and xq.is_cuda:
+        import torch
+
+        res.setDefaultStream(device, torch.cuda.current_stream(device).cuda_stream)
+    check(
+        lib.faiss_b200_bfKnn(
+            res._h, int(device), int(metric), ctypes.c_int64(k), int(d), _ptr(xb, _c_f), ctypes.c_int64(xb.shape[0]), _ptr(xq, _c_f),
+            ctypes.c_int64(nq), _ptr(D, _c_f), _ptr(I, _c_i64),
+        )
+    )
+    return D, I
+
+
 def kmeans_sharded(res, x_local, k, niter=25, seed=1234, device=0):
     """Collective: k-means over the rows of ALL ranks of the device's NCCL communicator (this rank passes its own
     rows; rank order = row order).  Returns (centroids [k, d] identical on every rank, objective per iteration,

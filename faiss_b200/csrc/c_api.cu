@@ -922,6 +922,32 @@ int b200_l2_norms(FaissStandardGpuResources* r, int device, const float* x, idx_
     }
     CATCH_AND_HANDLE
 }
+// bfKnn (faiss/gpu/GpuDistance.h:33-181, GpuDistance.cu:229-571) for the case on the path: row-major fp32 vectors and
+// queries, L2 or inner product, host or device pointers.  Large problems take the tensor-core path through a transient
+// GpuIndexFlat (vectors are copied once), small ones the exact SIMT kernel; results are identical either way.
+int faiss_b200_bfKnn(
+        FaissStandardGpuResources* r,
+        int device,
+        FaissMetricType metric,
+        idx_t k,
+        int dims,
+        const float* vectors,
+        idx_t num_vectors,
+        const float* queries,
+        idx_t num_queries,
+        float* out_distances,
+        idx_t* out_indices) {
+    try {
+        auto res = RES(r);
+        FB_THROW_IF_NOT_MSG(k >= 1 && k <= kMaxK, "bfKnn: k out of range");
+        GpuIndexFlatConfig cfg;
+        cfg.device = device;
+        GpuIndexFlat index(res, dims, MT(metric), cfg);
+        index.add(num_vectors, vectors);
+        index.search(num_queries, queries, k, out_distances, out_indices);
+    }
+    CATCH_AND_HANDLE
+}
 int b200_flat_search_exact(
         FaissStandardGpuResources* r,
         int device,

@@ -213,6 +213,11 @@ FB200_API int faiss_b200_kmeans_sharded(FaissStandardGpuResources* res, int devi
    k-means on the column slices of x [n,d] (host or device); centroids_out host [M][256][d/M] */
 FB200_API int faiss_b200_pq_train(FaissStandardGpuResources* res, int device, size_t d, size_t M, size_t n, const float* x, int niter, int seed, float* centroids_out);
 
+/* bfKnn (faiss/gpu/GpuDistance.h:33-181): brute-force k-NN of `queries` in `vectors` (both row-major fp32, host or
+   device), L2 or inner product; outputs host or device.  (Column-major inputs, fp16/bf16 vectors, other metrics and
+   bfKnn_tiling are not on the path.) */
+FB200_API int faiss_b200_bfKnn(FaissStandardGpuResources* res, int device, FaissMetricType metric, idx_t k, int dims, const float* vectors, idx_t num_vectors, const float* queries, idx_t num_queries, float* out_distances, idx_t* out_indices);
+
 /* ---- instrumentation (bench.py): kernels launched by this library so far; optional CUDA-event
    timing of a named kernel ("flat_tc") on its launching stream ---- */
 FB200_API long long faiss_b200_launch_count(void);

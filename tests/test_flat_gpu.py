@@ -274,3 +274,23 @@ def test_streaming_argmin_with_masses_of_ties(res):
     De, Ie = idx.search(xq, 1)
     assert np.array_equal(I, Ie) and np.array_equal(D, De)
     assert (D == 0).all() and (I < 64).all()
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+def test_bfknn_free_function(res, metric):
+    """faiss.knn_gpu / bfKnn (faiss/gpu/GpuDistance.h:33-181; the reference's TestGpuDistance.cu compares it with a
+    CPU IndexFlat the same way): host and device inputs, same tolerance as the index path."""
+    import torch
+
+    import faiss_b200 as fb
+
+    N, d, nq, k = 4000, 40, 37, 20
+    xb = o.float_rand(N * d, 77).reshape(N, d)
+    xq = o.float_rand(nq * d, 78).reshape(nq, d)
+    D, I = fb.bfKnn(res, xq, xb, k, metric)
+    rD, rI = _ref_search(xb, xq, k, metric)
+    o.compare_lists(rD, rI, D, I, eps=1e-4, pct_max_diff1=0.01, pct_max_diffN=0.002)
+    Dd, Id = fb.bfKnn(res, torch.from_numpy(xq).cuda(), torch.from_numpy(xb).cuda(), k, metric)
+    assert np.array_equal(I, Id.cpu().numpy()) and np.array_equal(D, Dd.cpu().numpy())
+    with pytest.raises(fb.FaissError):
+        fb.bfKnn(res, xq, xb, 5000, metric)

@@ -458,3 +458,26 @@ def test_index_shards_ivf_common_quantizer(res, golden):
     assert shards.ntotal == N
     D, I = shards.search(xq, k)
     o.compare_lists(golden["ivfpq_l2_D"], golden["ivfpq_l2_I"], D, I, eps=2e-4, pct_max_diff1=0.02, pct_max_diffN=0.01)
+
+
+@pytest.mark.parametrize("M", [32, 16])
+def test_ivfpq_k2048(res, M):
+    """k = 2048 (the documented GPU limit, faiss/gpu/utils/DeviceDefs.cuh:61-68) through the interleaved scan: the
+    CTA-wide list holds it (round 1 ran out of shared memory above k = 1024)"""
+    import faiss_b200 as fb
+
+    rs = np.random.RandomState(M)
+    N, d, nlist, k, nprobe = 60000, 64, 16, 2048, 8
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(12, d).astype(np.float32)
+    idx = fb.GpuIndexIVFPQ(res, d, nlist, M, 8)
+    idx.setClustering(niter=4)
+    idx.setPQClustering(niter=4)
+    idx.train(xb[:20000])
+    idx.add(xb)
+    idx.nprobe = nprobe
+    D, I = idx.search(xq, k)
+    lc = [idx.getListVectorData(l) for l in range(nlist)]
+    li = [idx.getListIndices(l) for l in range(nlist)]
+    rD, rI = o.ivfpq_search(xq, k, nprobe, idx.getCoarseCentroids(), idx.getPQCentroids(), lc, li, o.METRIC_L2)
+    o.compare_lists(rD, rI, D, I, eps=2e-4, pct_max_diff1=0.03, pct_max_diffN=0.015)
