@@ -210,6 +210,15 @@ class Index:
         self._use_torch_stream(x, ids)
         check(lib.faiss_Index_add_with_ids(self._h, ctypes.c_int64(x.shape[0]), _ptr(x, _c_f), _ptr(ids, _c_i64)))
 
+    def setMinPagingSize(self, size):
+        """GpuIndex::setMinPagingSize (faiss/gpu/GpuIndex.h:66-69)"""
+        check(lib.faiss_GpuIndex_setMinPagingSize(self._h, ctypes.c_size_t(size)))
+
+    def getMinPagingSize(self):
+        out = ctypes.c_size_t()
+        check(lib.faiss_GpuIndex_getMinPagingSize(self._h, ctypes.byref(out)))
+        return int(out.value)
+
     def search(self, x, k, D=None, I=None, params=None):
         """params: a SearchParametersIVF (per-call nprobe) or None -- faiss::Index::search(..., params)"""
         x = self._check_x(x)
@@ -310,12 +319,13 @@ def set_interrupt_callback(fn):
 class GpuIndexFlat(Index):
     """faiss::gpu::GpuIndexFlat (faiss/gpu/GpuIndexFlat.h:43-141)."""
 
-    def __init__(self, res, d, metric=METRIC_L2, device=0, use_tensor_cores=True):
+    def __init__(self, res, d, metric=METRIC_L2, device=0, use_tensor_cores=True, use_float16=False):
         super().__init__()
         self._keep.append(res)
         check(
-            lib.faiss_GpuIndexFlat_new(
-                ctypes.byref(self._h), res._h, int(d), int(metric), int(device), int(bool(use_tensor_cores))
+            lib.faiss_GpuIndexFlat_new_with_config(
+                ctypes.byref(self._h), res._h, int(d), int(metric), int(device), int(bool(use_tensor_cores)),
+                int(bool(use_float16)),
             )
         )
 
@@ -338,13 +348,13 @@ class GpuIndexFlat(Index):
 
 
 class GpuIndexFlatL2(GpuIndexFlat):
-    def __init__(self, res, d, device=0, use_tensor_cores=True):
-        super().__init__(res, d, METRIC_L2, device, use_tensor_cores)
+    def __init__(self, res, d, device=0, use_tensor_cores=True, use_float16=False):
+        super().__init__(res, d, METRIC_L2, device, use_tensor_cores, use_float16)
 
 
 class GpuIndexFlatIP(GpuIndexFlat):
-    def __init__(self, res, d, device=0, use_tensor_cores=True):
-        super().__init__(res, d, METRIC_INNER_PRODUCT, device, use_tensor_cores)
+    def __init__(self, res, d, device=0, use_tensor_cores=True, use_float16=False):
+        super().__init__(res, d, METRIC_INNER_PRODUCT, device, use_tensor_cores, use_float16)
 
 
 class GpuIndexIVF(Index):

@@ -72,12 +72,13 @@ void B200Index::reconstruct_n(faiss::idx_t i0, faiss::idx_t ni, float* recons) c
 }
 
 // ---------------------------------------------------------------- Flat
-B200IndexFlat::B200IndexFlat(B200Resources* res, int dims, faiss::MetricType metric, int device) : B200Index(dims, metric, device) {
-    ck(faiss_GpuIndexFlat_new(&h_, res->handle(), dims, mt(metric), device, 1));
+B200IndexFlat::B200IndexFlat(B200Resources* res, int dims, faiss::MetricType metric, int device, bool useFloat16)
+        : B200Index(dims, metric, device) {
+    ck(faiss_GpuIndexFlat_new_with_config(&h_, res->handle(), dims, mt(metric), device, 1, useFloat16 ? 1 : 0));
     sync_();
 }
-B200IndexFlat::B200IndexFlat(B200Resources* res, const faiss::IndexFlat* index, int device)
-        : B200IndexFlat(res, index->d, index->metric_type, device) {
+B200IndexFlat::B200IndexFlat(B200Resources* res, const faiss::IndexFlat* index, int device, bool useFloat16)
+        : B200IndexFlat(res, index->d, index->metric_type, device, useFloat16) {
     copyFrom(index);
 }
 void B200IndexFlat::copyFrom(const faiss::IndexFlat* index) { // faiss/gpu/GpuIndexFlat.cu:105-140
@@ -218,9 +219,9 @@ void B200IndexIVFPQ::copyTo(faiss::IndexIVFPQ* index) const { // faiss/gpu/GpuIn
 }
 
 // ---------------------------------------------------------------- cloner
-faiss::Index* index_cpu_to_b200(B200Resources* res, int device, const faiss::Index* index) {
+faiss::Index* index_cpu_to_b200(B200Resources* res, int device, const faiss::Index* index, const B200ClonerOptions* options) {
     if (auto* f = dynamic_cast<const faiss::IndexFlat*>(index))
-        return new B200IndexFlat(res, f, device);
+        return new B200IndexFlat(res, f, device, options && options->useFloat16);
     if (auto* pq = dynamic_cast<const faiss::IndexIVFPQ*>(index))
         return new B200IndexIVFPQ(res, pq, device);
     if (auto* fl = dynamic_cast<const faiss::IndexIVFFlat*>(index))

@@ -74,8 +74,9 @@ class B200Index : public faiss::Index {
 
 class B200IndexFlat : public B200Index { // faiss::gpu::GpuIndexFlat (faiss/gpu/GpuIndexFlat.h:43-141)
    public:
-    B200IndexFlat(B200Resources* res, int dims, faiss::MetricType metric, int device = 0);
-    B200IndexFlat(B200Resources* res, const faiss::IndexFlat* index, int device = 0);
+    // useFloat16: GpuIndexFlatConfig::useFloat16 (faiss/gpu/GpuIndexFlat.h:26-35) -- fp16 storage, queries rounded to fp16
+    B200IndexFlat(B200Resources* res, int dims, faiss::MetricType metric, int device = 0, bool useFloat16 = false);
+    B200IndexFlat(B200Resources* res, const faiss::IndexFlat* index, int device = 0, bool useFloat16 = false);
     void copyFrom(const faiss::IndexFlat* index);
     void copyTo(faiss::IndexFlat* index) const;
 };
@@ -116,7 +117,11 @@ class B200IndexIVFPQ : public B200IndexIVF { // faiss/gpu/GpuIndexIVFPQ.h:56-181
 };
 
 // faiss::gpu::index_cpu_to_gpu / index_gpu_to_cpu (faiss/gpu/GpuCloner.cpp:124-255) for the three index types on the path
-faiss::Index* index_cpu_to_b200(B200Resources* res, int device, const faiss::Index* index);
+// the fields of GpuClonerOptions (faiss/gpu/GpuClonerOptions.h:17-56) that act on this path
+struct B200ClonerOptions {
+    bool useFloat16 = false; // Flat: fp16 storage
+};
+faiss::Index* index_cpu_to_b200(B200Resources* res, int device, const faiss::Index* index, const B200ClonerOptions* options = nullptr);
 faiss::Index* index_b200_to_cpu(const faiss::Index* index);
 
 } // namespace faiss_b200_adapter

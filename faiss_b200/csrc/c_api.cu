@@ -270,6 +270,27 @@ int faiss_GpuIndexFlat_new(
     }
     CATCH_AND_HANDLE
 }
+int faiss_GpuIndexFlat_new_with_config(
+        FaissGpuIndex** p,
+        FaissStandardGpuResources* r,
+        int d,
+        FaissMetricType metric,
+        int device,
+        int use_tc,
+        int use_float16) {
+    try {
+        GpuIndexFlatConfig c;
+        c.device = device;
+        c.useTensorCores = use_tc != 0;
+        c.useFloat16 = use_float16 != 0;
+        auto res = RES(r);
+        auto* h = new FaissIndex_H();
+        h->res = res;
+        h->index = new GpuIndexFlat(res, d, MT(metric), c);
+        *p = h;
+    }
+    CATCH_AND_HANDLE
+}
 int faiss_GpuIndexFlatL2_new(FaissGpuIndex** p, FaissStandardGpuResources* r, int d, int device) {
     return faiss_GpuIndexFlat_new(p, r, d, ::METRIC_L2, device, 1);
 }
@@ -285,6 +306,18 @@ int faiss_GpuIndexFlat_copyFrom(FaissGpuIndex* p, idx_t n, const float* xb) {
 int faiss_GpuIndexFlat_copyTo(const FaissGpuIndex* p, float* out) {
     try {
         AS<GpuIndexFlat>(p, "GpuIndexFlat")->copyTo(out);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndex_setMinPagingSize(FaissGpuIndex* p, size_t size) { // faiss/gpu/GpuIndex.h:66-69
+    try {
+        AS<GpuIndex>(p, "GpuIndex")->setMinPagingSize(size);
+    }
+    CATCH_AND_HANDLE
+}
+int faiss_GpuIndex_getMinPagingSize(const FaissGpuIndex* p, size_t* out) {
+    try {
+        *out = AS<GpuIndex>(p, "GpuIndex")->getMinPagingSize();
     }
     CATCH_AND_HANDLE
 }

@@ -12,6 +12,8 @@
 // expression, so both paths return bit-identical distances.
 #include <cfloat>
 
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 #include "select.cuh"
 
@@ -66,7 +68,8 @@ template <int TQ, int TN, bool IS_L2, bool K1>
 __global__ void __launch_bounds__(256) flat_exact_kernel(
         const float* __restrict__ Q,
         int nq,
-        const float* __restrict__ Y,
+        const void* __restrict__ Yv, // [n][d] fp32, or fp16 when yHalf (useFloat16 storage: widened on load, same arithmetic)
+        int yHalf,
         int64_t n,
         int d,
         int k,
@@ -122,6 +125,8 @@ __global__ void __launch_bounds__(256) flat_exact_kernel(
     __syncthreads();
 
     const bool vec4 = ((d & 3) == 0);
+    const float* Y = reinterpret_cast<const float*>(Yv);
+    const __half* Yh = reinterpret_cast<const __half*>(Yv);
 
     for (int64_t nb = r0; nb < r1; nb += TN) {
         float acc[C::RQ][4];
@@ -143,11 +148,30 @@ __global__ void __launch_bounds__(256) flat_exact_kernel(
                     if (q0 + row < nq)
                         src = Q + (int64_t)(q0 + row) * d;
                 } else {
-                    if (nb + row < r1)
+                    if (nb + row < r1 && !yHalf)
                         src = Y + (nb + row) * d;
                 }
                 int col = kk + c4 * 4;
-                if (src) {
+                if (!isQ && yHalf) {
+                    if (nb + row < r1) {
+                        const __half* hs = Yh + (nb + row) * d;
+                        if (vec4 && col + 3 < d) {
+                            const uint2 u = *reinterpret_cast<const uint2*>(hs + col);
+                            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                            v = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        } else {
+                            if (col + 0 < d)
+                                v.x = __half2float(hs[col + 0]);
+                            if (col + 1 < d)
+                                v.y = __half2float(hs[col + 1]);
+                            if (col + 2 < d)
+                                v.z = __half2float(hs[col + 2]);
+                            if (col + 3 < d)
+                                v.w = __half2float(hs[col + 3]);
+                        }
+                    }
+                } else if (src) {
                     if (vec4 && col + 3 < d) {
                         v = *reinterpret_cast<const float4*>(src + col);
                     } else {
@@ -435,7 +459,8 @@ template <int TQ, int TN, bool K1>
 static void launchExact(
         const float* Q,
         int64_t nq,
-        const float* Y,
+        const void* Y,
+        int yHalf,
         int64_t n,
         int d,
         int k,
@@ -454,11 +479,11 @@ static void launchExact(
     if (metric == METRIC_L2) {
         auto kern = flat_exact_kernel<TQ, TN, true, K1>;
         CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, C::kThreads, smem, stream>>>(Q, (int)nq, Y, n, d, k, LIST, rowsPerSplit, partD, partI);
+        kern<<<grid, C::kThreads, smem, stream>>>(Q, (int)nq, Y, yHalf, n, d, k, LIST, rowsPerSplit, partD, partI);
     } else {
         auto kern = flat_exact_kernel<TQ, TN, false, K1>;
         CUDA_VERIFY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, C::kThreads, smem, stream>>>(Q, (int)nq, Y, n, d, k, LIST, rowsPerSplit, partD, partI);
+        kern<<<grid, C::kThreads, smem, stream>>>(Q, (int)nq, Y, yHalf, n, d, k, LIST, rowsPerSplit, partD, partI);
     }
     CUDA_CHECK_LAST();
 }
@@ -468,7 +493,8 @@ static void flatExactImpl(
         int device,
         const float* Q,
         int64_t nq,
-        const float* Y,
+        const void* Y,
+        int yHalf,
         int64_t n,
         int d,
         int k,
@@ -519,7 +545,7 @@ static void flatExactImpl(
 
 #define LAUNCH(TQ_, TN_, K1_)                                                                        \
     launchExact<TQ_, TN_, K1_>(                                                                      \
-            Q, nq, Y, n, d, k, LIST, metric, (int)nsplit, rowsPerSplit, partD.as<float>(), partI.as<idx_t>(), stream)
+            Q, nq, Y, yHalf, n, d, k, LIST, metric, (int)nsplit, rowsPerSplit, partD.as<float>(), partI.as<idx_t>(), stream)
     if (K1) {
         LAUNCH(32, 64, true);
     } else if (TQ == 32) {
@@ -539,7 +565,7 @@ void runFlatExact(
         int device,
         const float* Q,
         int64_t nq,
-        const float* Y,
+        const void* Y,
         int64_t n,
         int d,
         int k,
@@ -547,8 +573,9 @@ void runFlatExact(
         int64_t idBase,
         float* outD,
         idx_t* outI,
-        cudaStream_t stream) {
-    flatExactImpl(res, device, Q, nq, Y, n, d, k, metric, idBase, outD, outI, stream);
+        cudaStream_t stream,
+        int yHalf) {
+    flatExactImpl(res, device, Q, nq, Y, yHalf, n, d, k, metric, idBase, outD, outI, stream);
 }
 
 void runFlatArgmin(
@@ -570,15 +597,20 @@ void runFlatArgmin(
         tmp = res->temp(device, sizeof(float) * nq);
         outD = tmp.as<float>();
     }
-    flatExactImpl(res, device, Q, nq, Y, n, d, 1, metric, 0, outD, outI, stream);
+    flatExactImpl(res, device, Q, nq, Y, 0, n, d, 1, metric, 0, outD, outI, stream);
 }
 
 // ------------------------------------------------------------------------------------------
 // residual / gather
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float row_elem(const void* base, int yHalf, int64_t idx) {
+    return yHalf ? __half2float(reinterpret_cast<const __half*>(base)[idx]) : reinterpret_cast<const float*>(base)[idx];
+}
+
 __global__ void calc_residual_kernel(
         const float* __restrict__ x,
-        const float* __restrict__ c,
+        const void* __restrict__ c,
+        int yHalf,
         const idx_t* __restrict__ assign,
         int64_t n,
         int d,
@@ -586,27 +618,29 @@ __global__ void calc_residual_kernel(
     int64_t i = blockIdx.x;
     idx_t a = assign[i];
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        out[i * d + j] = (a < 0) ? CUDART_NAN_F : x[i * d + j] - c[a * d + j]; // VectorResidual.cu:26-60
+        out[i * d + j] = (a < 0) ? CUDART_NAN_F : x[i * d + j] - row_elem(c, yHalf, a * d + j); // VectorResidual.cu:26-60
     }
 }
 
 void runCalcResidual(
         const float* x,
-        const float* centroids,
+        const void* centroids,
         const idx_t* assign,
         int64_t n,
         int d,
         float* out,
-        cudaStream_t stream) {
+        cudaStream_t stream,
+        int yHalf) {
     if (n == 0)
         return;
     FB_THROW_IF_NOT(n < (int64_t(1) << 31));
-    calc_residual_kernel<<<(unsigned)n, std::min(d, 256), 0, stream>>>(x, centroids, assign, n, d, out);
+    calc_residual_kernel<<<(unsigned)n, std::min(d, 256), 0, stream>>>(x, centroids, yHalf, assign, n, d, out);
     CUDA_CHECK_LAST();
 }
 
 __global__ void gather_rows_kernel(
-        const float* __restrict__ src,
+        const void* __restrict__ src,
+        int yHalf,
         const idx_t* __restrict__ ids,
         int64_t n,
         int d,
@@ -614,15 +648,15 @@ __global__ void gather_rows_kernel(
     int64_t i = blockIdx.x;
     idx_t a = ids[i];
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
-        out[i * d + j] = a < 0 ? CUDART_NAN_F : src[a * d + j];
+        out[i * d + j] = a < 0 ? CUDART_NAN_F : row_elem(src, yHalf, a * d + j);
     }
 }
 
-void runGatherRows(const float* src, const idx_t* ids, int64_t n, int d, float* out, cudaStream_t stream) {
+void runGatherRows(const void* src, const idx_t* ids, int64_t n, int d, float* out, cudaStream_t stream, int yHalf) {
     if (n == 0)
         return;
     FB_THROW_IF_NOT(n < (int64_t(1) << 31));
-    gather_rows_kernel<<<(unsigned)n, std::min(d, 256), 0, stream>>>(src, ids, n, d, out);
+    gather_rows_kernel<<<(unsigned)n, std::min(d, 256), 0, stream>>>(src, yHalf, ids, n, d, out);
     CUDA_CHECK_LAST();
 }
 

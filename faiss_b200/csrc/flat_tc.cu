@@ -54,10 +54,29 @@ using namespace tc;
 // ------------------------------------------------------------------------------------------
 // small helper kernels
 // ------------------------------------------------------------------------------------------
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t count, float* out) {
+// database rows as stored: fp32, or fp16 under GpuIndexFlatConfig::useFloat16 (widened on load; every kernel below
+// then runs the same fp32 arithmetic on the widened values)
+template <bool YH>
+__device__ __forceinline__ float row_load1(const void* base, int64_t idx) {
+    if (YH)
+        return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+    return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+template <bool YH>
+__device__ __forceinline__ float4 row_load4(const void* base, int64_t idx) { // idx % 4 == 0, row start 8 / 16 B aligned
+    if (YH) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + idx));
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+}
+
+__global__ void absmax_kernel(const void* __restrict__ x, int yHalf, int64_t count, float* out) {
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = fabsf(x[i]);
+        float v = fabsf(yHalf ? row_load1<true>(x, i) : reinterpret_cast<const float*>(x)[i]);
         if (v == v && v <= FLT_MAX) // ignore NaN / inf for the scale
             m = fmaxf(m, v);
     }
@@ -70,7 +89,8 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t count, float*
 
 // rows -> fp16 (scaled, zero padded to dpad) + bias + norms ; one warp per row
 __global__ void tc_prepare_rows_kernel(
-        const float* __restrict__ Y,
+        const void* __restrict__ Y,
+        int yHalf,
         int64_t n,
         int d,
         int dpad,
@@ -83,11 +103,11 @@ __global__ void tc_prepare_rows_kernel(
     int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n)
         return;
-    const float* src = Y + (perm ? (int64_t)perm[row] : row) * d;
+    const int64_t src = (perm ? (int64_t)perm[row] : row) * d;
     __half* dst = Y16 + row * dpad;
     float acc = 0.f;
     for (int i = lane_id(); i < dpad; i += 32) {
-        float v = i < d ? src[i] : 0.f;
+        float v = i < d ? (yHalf ? row_load1<true>(Y, src + i) : reinterpret_cast<const float*>(Y)[src + i]) : 0.f;
         acc = fmaf(v, v, acc);
         if (Y16)
             dst[i] = __float2half_rn(v * scale);
@@ -492,7 +512,7 @@ __global__ void tc_pooled_thr_kernel(int nq, const float* __restrict__ contrib, 
 }
 
 // exact re-rank of the base list with the canonical fp32 arithmetic; output sorted by (dist, id)
-template <bool IS_L2>
+template <bool IS_L2, bool YH>
 __global__ void tc_rerank_kernel(
         int nq,
         int d,
@@ -500,7 +520,7 @@ __global__ void tc_rerank_kernel(
         int LIST,
         int KL, // output list size (pow2 >= k, >= 64)
         const float* __restrict__ Q,
-        const float* __restrict__ Y,
+        const void* __restrict__ Y,
         const int* __restrict__ perm, // stored (norm-sorted) position -> row id; null: identity
         const int* __restrict__ baseId,
         const float* __restrict__ baseKey, // with thr: entries whose approximate score is <= thr[q] are skipped
@@ -529,7 +549,7 @@ __global__ void tc_rerank_kernel(
             id = perm[id];
         float acc = 0.f;
         if (valid) {
-            const float* yp = Y + (int64_t)id * d;
+            const int64_t yo = (int64_t)id * d;
             // canonical order: sequential FMA over the dimension (loads vectorised, math not reordered)
             int i = 0;
             if ((d & 3) == 0) {
@@ -537,7 +557,7 @@ __global__ void tc_rerank_kernel(
 #pragma unroll 8
                 for (; i < d; i += 4) {
                     const float4 a4 = *reinterpret_cast<const float4*>(qp + i);
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(yp + i));
+                    const float4 b4 = row_load4<YH>(Y, yo + i);
                     const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
@@ -552,7 +572,7 @@ __global__ void tc_rerank_kernel(
                 }
             }
             for (; i < d; i++) {
-                float a = qp[i], b = yp[i];
+                float a = qp[i], b = row_load1<YH>(Y, yo + i);
                 if (IS_L2) {
                     float df = a - b;
                     acc = fmaf(df, df, acc);
@@ -591,7 +611,7 @@ __global__ void tc_init_base_kernel(float* baseKey, int* baseId, int64_t count) 
 // gets its canonical fp32 distance -- one lane per candidate, sequential FMA over the dimension exactly like
 // flat_exact.cu -- (3) the (distance, id) minimum is the answer.  A segment that overflowed flags the query for
 // the exact kernel.
-template <bool IS_L2>
+template <bool IS_L2, bool YH>
 __global__ void tc_argmin_finish_kernel(
         int nq,
         int d,
@@ -602,7 +622,7 @@ __global__ void tc_argmin_finish_kernel(
         const int* __restrict__ candCount,
         const float* __restrict__ eps,
         const float* __restrict__ Q,
-        const float* __restrict__ Y,
+        const void* __restrict__ Y,
         const int* __restrict__ perm,
         float* __restrict__ outD,
         idx_t* __restrict__ outI,
@@ -650,10 +670,10 @@ __global__ void tc_argmin_finish_kernel(
                 int id = (int)v.y;
                 if (perm)
                     id = perm[id];
-                const float* yp = Y + (int64_t)id * d;
+                const int64_t yo = (int64_t)id * d;
                 float acc = 0.f;
                 for (int i = 0; i < d; i++) {
-                    const float a = qp[i], b = __ldg(yp + i);
+                    const float a = qp[i], b = row_load1<YH>(Y, yo + i);
                     if (IS_L2) {
                         const float df = a - b;
                         acc = fmaf(df, df, acc);
@@ -750,11 +770,12 @@ PFN_encodeTiled getEncodeTiled() {
 
 // fp16 matrix [rows][dpad] viewed as (64, rows, dpad/64); one box = (64, 128, dpad/64) = a full
 // K-extent tile laid out [kblock][row][64] with the 128-byte swizzle the UMMA descriptors expect.
-CUtensorMap makeTileMap(const __half* base, int64_t rows, int dpad, int boxRows) {
+// boxK = 0: the box spans every K-block (a whole tile); boxK = 1: one K-block per copy (K-split database stages).
+CUtensorMap makeTileMap(const __half* base, int64_t rows, int dpad, int boxRows, int boxK = 0) {
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)kKBlock, (cuuint64_t)rows, (cuuint64_t)(dpad / kKBlock)};
     cuuint64_t strides[2] = {(cuuint64_t)dpad * 2, (cuuint64_t)kKBlock * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)boxRows, (cuuint32_t)(dpad / kKBlock)};
+    cuuint32_t box[3] = {(cuuint32_t)kKBlock, (cuuint32_t)boxRows, (cuuint32_t)(boxK > 0 ? boxK : dpad / kKBlock)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = getEncodeTiled()(
             &m,
@@ -785,16 +806,26 @@ unsigned long long gcd64(unsigned long long a, unsigned long long b) {
 struct SmemPlan {
     int yStages;
     size_t bytes;
+    int ksplit; // ring stages hold single K-blocks (see flat_tc_kernel)
 };
 
+constexpr int kMaxKB = 4; // d <= 256: two query tiles (32 KB per K-block) + at least three 32 KB K-block stages in 227 KB
+
 SmemPlan planSmem(int KB) {
-    const size_t stage = (size_t)KB * kTileN * kKBlock * 2;
     const size_t qtiles = (size_t)2 * KB * kTileM * kKBlock * 2;
-    const size_t budget = 220 * 1024;
     const size_t fixed = 1024 /*align slack*/ + 512 /*barriers*/ + qtiles;
+    if (KB <= 2) {
+        const size_t stage = (size_t)KB * kTileN * kKBlock * 2;
+        const size_t budget = 220 * 1024;
+        int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
+        return {ys, fixed + ys * stage, 0};
+    }
+    FB_THROW_IF_NOT_MSG(KB <= kMaxKB, "dimension too large for the tensor-core Flat kernel");
+    const size_t stage = (size_t)kTileN * kKBlock * 2;
+    const size_t budget = 226 * 1024; // 232448 B is the opt-in limit per CTA
     int ys = (int)std::min<size_t>(kMaxYStages, (budget - fixed) / stage);
-    FB_THROW_IF_NOT_MSG(ys >= 2, "dimension too large for the tensor-core Flat kernel");
-    return {ys, fixed + ys * stage};
+    FB_THROW_IF_NOT(ys >= 3);
+    return {ys, fixed + ys * stage, 1};
 }
 
 // column parts per tile = epilogue warps / 4 (FB200_TC_PARTS: tuning knob, 2 or 4)
@@ -824,22 +855,22 @@ void launchTc(const CUtensorMap& mq, const CUtensorMap& my, const TcParams& p, i
 // ------------------------------------------------------------------------------------------
 // public launchers
 // ------------------------------------------------------------------------------------------
-void runAbsMax(const float* x, int64_t count, float* out, cudaStream_t stream) {
+void runAbsMax(const void* x, int64_t count, float* out, cudaStream_t stream, int yHalf) {
     if (count == 0)
         return;
     int blocks = (int)std::min<int64_t>(1184, ceil_div(count, 256));
-    absmax_kernel<<<blocks, 256, 0, stream>>>(x, count, out);
+    absmax_kernel<<<blocks, 256, 0, stream>>>(x, yHalf, count, out);
     CUDA_CHECK_LAST();
 }
 
 void runMaxOf(const float* x, int64_t count, float* out, cudaStream_t stream) {
-    runAbsMax(x, count, out, stream);
+    runAbsMax(x, count, out, stream, 0);
 }
 
 void runFlatTcPrepareRows(
         GpuResources* res,
         int device,
-        const float* Y,
+        const void* Y,
         int64_t n,
         int d,
         int dpad,
@@ -850,14 +881,15 @@ void runFlatTcPrepareRows(
         int* perm,
         float* tileMaxBias,
         float* norms,
-        cudaStream_t stream) {
+        cudaStream_t stream,
+        int yHalf) {
     if (n == 0)
         return;
     const int warps = 8;
     const unsigned rowBlocks = (unsigned)ceil_div(n, warps);
     const int isL2 = metric == METRIC_L2 ? 1 : 0;
     // squared norms in row order (also feeds the caller's max-norm reduction)
-    tc_prepare_rows_kernel<<<rowBlocks, warps * 32, 0, stream>>>(Y, n, d, dpad, scale, isL2, nullptr, nullptr, nullptr, norms);
+    tc_prepare_rows_kernel<<<rowBlocks, warps * 32, 0, stream>>>(Y, yHalf, n, d, dpad, scale, isL2, nullptr, nullptr, nullptr, norms);
     CUDA_CHECK_LAST();
     if (perm) {
         // stored order = rows sorted by squared norm: the biases of a 256-row tile are then nearly
@@ -873,7 +905,7 @@ void runFlatTcPrepareRows(
         CUDA_VERIFY(cub::DeviceRadixSort::SortPairs(
                 tmp.data, tmpBytes, norms, keysOut.as<float>(), valsIn.as<int>(), perm, (int)n, 0, 32, stream));
     }
-    tc_prepare_rows_kernel<<<rowBlocks, warps * 32, 0, stream>>>(Y, n, d, dpad, scale, isL2, perm, Y16, bias, nullptr);
+    tc_prepare_rows_kernel<<<rowBlocks, warps * 32, 0, stream>>>(Y, yHalf, n, d, dpad, scale, isL2, perm, Y16, bias, nullptr);
     CUDA_CHECK_LAST();
     const int64_t numTiles = ceil_div(n, kTileN);
     tc_tile_max_bias_kernel<<<(unsigned)ceil_div(numTiles, warps), warps * 32, 0, stream>>>(bias, numTiles, tileMaxBias);
@@ -884,7 +916,7 @@ bool flatTcSupported(int d, int k, int64_t n) {
     int dpad = (int)round_up(d, kKBlock);
     // k = 1 takes the streaming mode, which pays off from a few tiles on (coarse assignment against nlist >= 2048
     // centroids during add / k-means); the round-based path needs a database worth several rounds
-    return dpad <= 128 && k >= 1 && k <= 512 && n >= (k == 1 ? 2048 : 32768) && n < (int64_t(1) << 31) - 512;
+    return dpad <= kMaxKB * kKBlock && k >= 1 && k <= 2048 && n >= (k == 1 ? 2048 : 32768) && n < (int64_t(1) << 31) - 512;
 }
 
 void runFlatTcScoresDebug(
@@ -895,10 +927,10 @@ void runFlatTcScoresDebug(
         int dpad,
         float* S,
         cudaStream_t stream) {
-    FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= 128);
+    FB_THROW_IF_NOT(dpad % kKBlock == 0 && dpad <= kMaxKB * kKBlock);
     const int KB = dpad / kKBlock;
     SmemPlan sp = planSmem(KB);
-    CUtensorMap my = makeTileMap(Y16, n, dpad, kTileN);
+    CUtensorMap my = makeTileMap(Y16, n, dpad, kTileN, sp.ksplit);
     const int64_t numTiles = ceil_div(n, kTileN);
     const int64_t qPairs = ceil_div(nq, kPairM);
     // the kernel reads whole 256-row query pairs: zero-padded private copy
@@ -923,6 +955,7 @@ void runFlatTcScoresDebug(
     p.permB = 0;
     p.numTiles = (unsigned long long)numTiles;
     p.KB = KB;
+    p.ksplit = sp.ksplit;
     p.yStages = sp.yStages;
     p.invScalePtr = one;
     p.bias = nullptr;
@@ -947,7 +980,7 @@ void runFlatTcSearch(
         int device,
         const float* Q,
         int64_t nqAll,
-        const float* Y,
+        const void* Y,
         const __half* Y16,
         const float* bias,
         const int* perm,
@@ -962,7 +995,8 @@ void runFlatTcSearch(
         float* outD,
         idx_t* outI,
         cudaStream_t stream,
-        const FlatTcShard* shard) {
+        const FlatTcShard* shard,
+        int yHalf) {
     if (nqAll == 0)
         return;
     FB_THROW_IF_NOT(flatTcSupported(d, k, n));
@@ -992,7 +1026,7 @@ void runFlatTcSearch(
     const float c1 = 1.01f * (ldexpf(1.f, -10) + (float)dpad * ldexpf(1.f, -22));
     const float c2 = (float)(dpad + 16) * ldexpf(1.f, -24);
 
-    CUtensorMap mapY = makeTileMap(Y16, n, dpad, kTileN);
+    CUtensorMap mapY = makeTileMap(Y16, n, dpad, kTileN, sp.ksplit);
 
     // first round: ~40 k rows (16 tiles at k = 100).  Every score of round 0 becomes a candidate, so a
     // fixed 16 tiles would make small-k searches (k-means assignment: k = 1, millions of queries) pay 4096
@@ -1015,8 +1049,10 @@ void runFlatTcSearch(
     static const bool noStream = getenv("FB200_TC_NO_STREAM") && atoi(getenv("FB200_TC_NO_STREAM")) != 0;
     const bool streaming = k == 1 && !shard && !noStream;
     // streaming: a batch is a whole number of waves of the persistent grid (one 256-query unit per CTA and wave)
+    // (large k: the all-pass round covers 40 k rows, so the floor drops to keep the arena near 1 GiB)
+    const int64_t kQFloor = r0Tiles > 64 ? 2048 : 16384;
     const int64_t kQBatch = streaming ? (int64_t)sms * kPairM * 4
-                                      : std::min<int64_t>(131072, std::max<int64_t>(16384, (int64_t)kPairM * 1024 / r0Tiles));
+                                      : std::min<int64_t>(131072, std::max<int64_t>(kQFloor, (int64_t)kPairM * 1024 / r0Tiles));
     for (int64_t qb = 0; qb < nqAll; qb += kQBatch) {
         const int64_t nq = std::min(kQBatch, nqAll - qb);
         const float* Qb = Q + qb * d;
@@ -1129,6 +1165,7 @@ void runFlatTcSearch(
             p.permB = B;
             p.numTiles = (unsigned long long)T;
             p.KB = KB;
+            p.ksplit = sp.ksplit;
             p.yStages = sp.yStages;
             p.invScalePtr = sc + 2;
             p.bias = bias;
@@ -1152,14 +1189,15 @@ void runFlatTcSearch(
                 float* oD1 = outD + qb;
                 idx_t* oI1 = outI + qb;
                 KernelTiming::begin("tc_argmin_finish", stream);
+                auto launchFin = [&](auto kern) {
+                    kern<<<(unsigned)ceil_div(nq, fw), fw * 32, 0, stream>>>(
+                            (int)nq, d, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(), Qb, Y, perm,
+                            oD1, oI1, flags.as<int>());
+                };
                 if (metric == METRIC_L2)
-                    tc_argmin_finish_kernel<true><<<(unsigned)ceil_div(nq, fw), fw * 32, 0, stream>>>(
-                            (int)nq, d, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(), Qb, Y, perm,
-                            oD1, oI1, flags.as<int>());
+                    yHalf ? launchFin(tc_argmin_finish_kernel<true, true>) : launchFin(tc_argmin_finish_kernel<true, false>);
                 else
-                    tc_argmin_finish_kernel<false><<<(unsigned)ceil_div(nq, fw), fw * 32, 0, stream>>>(
-                            (int)nq, d, r.slices, parts, arena.as<uint2>(), r.cap, counts.as<int>(), eps.as<float>(), Qb, Y, perm,
-                            oD1, oI1, flags.as<int>());
+                    yHalf ? launchFin(tc_argmin_finish_kernel<false, true>) : launchFin(tc_argmin_finish_kernel<false, false>);
                 KernelTiming::end("tc_argmin_finish", stream);
                 CUDA_CHECK_LAST();
                 continue;
@@ -1220,9 +1258,9 @@ void runFlatTcSearch(
             };
             KernelTiming::begin("tc_rerank", stream);
             if (metric == METRIC_L2)
-                launchRr(tc_rerank_kernel<true>);
+                yHalf ? launchRr(tc_rerank_kernel<true, true>) : launchRr(tc_rerank_kernel<true, false>);
             else
-                launchRr(tc_rerank_kernel<false>);
+                yHalf ? launchRr(tc_rerank_kernel<false, true>) : launchRr(tc_rerank_kernel<false, false>);
             KernelTiming::end("tc_rerank", stream);
             CUDA_CHECK_LAST();
         }
@@ -1243,7 +1281,7 @@ void runFlatTcSearch(
                 auto fI = res->temp(device, sizeof(idx_t) * (size_t)nflag * k);
                 tc_gather_queries_kernel<<<nflag, 128, 0, stream>>>(Qb, list.as<int>(), d, fq.as<float>());
                 CUDA_CHECK_LAST();
-                runFlatExact(res, device, fq.as<float>(), nflag, Y, n, d, k, metric, 0, fD.as<float>(), fI.as<idx_t>(), stream);
+                runFlatExact(res, device, fq.as<float>(), nflag, Y, n, d, k, metric, 0, fD.as<float>(), fI.as<idx_t>(), stream, yHalf);
                 tc_scatter_results_kernel<<<nflag, 128, 0, stream>>>(
                         fD.as<float>(), fI.as<idx_t>(), list.as<int>(), k, outD + qb * k, outI + qb * k);
                 CUDA_CHECK_LAST();

@@ -55,6 +55,7 @@ struct TcParams {
     int tilesPerSlice;
     unsigned long long permA, permB, numTiles;
     int KB;             // dpad / 64
+    int ksplit;         // 1: a ring stage holds ONE 64-wide K-block of a database tile (128 < d <= 256), else a whole tile
     int yStages;
     const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
     const float* bias;  // [numTiles*256], -inf padded (read on the slow path only)
@@ -174,7 +175,10 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
     unsigned char* smem = reinterpret_cast<unsigned char*>(
             (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     const int qBytes = p.KB * kTileM * kKBlock * 2;     // one query tile   (128 rows)
-    const int stageBytes = p.KB * kTileN * kKBlock * 2; // one database tile (256 rows)
+    // one ring stage: a whole database tile (256 rows x dpad), or -- K-split mode, dpad > 128, where two query tiles plus
+    // whole-tile stages no longer fit 227 KB -- one 64-wide K-block of it.  K-split streams every tile once per
+    // accumulator (twice per unit): L2 -> SM traffic doubles, the roles and the epilogue stay exactly the same.
+    const int stageBytes = (p.ksplit ? 1 : p.KB) * kTileN * kKBlock * 2;
     unsigned char* sQ = smem;                            // two query tiles
     unsigned char* sY = smem + 2 * qBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sY + (size_t)p.yStages * stageBytes);
@@ -231,12 +235,16 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                 const int pe = min(p.tileEnd, pb + p.tilesPerSlice);
                 for (int pp = pb; pp < pe; pp++) {
                     const int t = perm_tile(p, pp);
-                    ptx::mbar_wait(&y_empty[ys], yphase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&y_full[ys], (uint32_t)stageBytes);
-                    ptx::tma_load_3d(sY + (size_t)ys * stageBytes, &mapY, &y_full[ys], 0, t * kTileN, 0);
-                    if (++ys == p.yStages) {
-                        ys = 0;
-                        yphase ^= 1;
+                    // K-split: mapY's box is one K-block; the tile goes through the ring once per accumulator
+                    const int loads = p.ksplit ? 2 * p.KB : 1;
+                    for (int l = 0; l < loads; l++) {
+                        ptx::mbar_wait(&y_empty[ys], yphase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&y_full[ys], (uint32_t)stageBytes);
+                        ptx::tma_load_3d(sY + (size_t)ys * stageBytes, &mapY, &y_full[ys], 0, t * kTileN, p.ksplit ? l % p.KB : 0);
+                        if (++ys == p.yStages) {
+                            ys = 0;
+                            yphase ^= 1;
+                        }
                     }
                 }
             }
@@ -259,6 +267,35 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                 ptx::mbar_wait(q_full, it & 1);
                 ptx::tc_fence_after();
                 for (int pp = pb; pp < pe; pp++) {
+                    if (p.ksplit) {
+                        // one ring stage per K-block, consumed in the producer's order (h outer, kb inner)
+#pragma unroll 1
+                        for (int h = 0; h < 2; h++) {
+                            ptx::mbar_wait(&t_empty[h], tphase ^ 1);
+                            ptx::tc_fence_after();
+                            const uint32_t dcol = tmem_base + (uint32_t)h * kTileN;
+                            const uint32_t qaddr = sQaddr + (uint32_t)h * (uint32_t)qBytes;
+                            for (int kb = 0; kb < p.KB; kb++) {
+                                ptx::mbar_wait(&y_full[ys], yphase);
+                                ptx::tc_fence_after();
+                                const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
+#pragma unroll
+                                for (int k4 = 0; k4 < 4; k4++) {
+                                    uint64_t da = ptx::make_smem_desc_sw128(qaddr + kb * qkb + k4 * 32);
+                                    uint64_t db = ptx::make_smem_desc_sw128(yaddr + k4 * 32);
+                                    ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
+                                }
+                                ptx::mma_commit(&y_empty[ys]);
+                                if (++ys == p.yStages) {
+                                    ys = 0;
+                                    yphase ^= 1;
+                                }
+                            }
+                            ptx::mma_commit(&t_full[h]);
+                        }
+                        tphase ^= 1;
+                        continue;
+                    }
                     ptx::mbar_wait(&y_full[ys], yphase);
                     ptx::tc_fence_after();
                     const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;

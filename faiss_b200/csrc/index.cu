@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstring>
 #include <future>
@@ -91,6 +92,21 @@ __global__ void iota_ids_kernel(idx_t* out, idx_t n, idx_t base) {
     if (i < n)
         out[i] = base + i;
 }
+// fp32 -> fp16 (round to nearest even), written as fp16 and / or widened back to fp32 (GpuIndexFlat useFloat16)
+__global__ void float_to_half_kernel(const float* __restrict__ x, __half* __restrict__ out16, float* __restrict__ out32, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const __half h = __float2half_rn(x[i]);
+        if (out16)
+            out16[i] = h;
+        if (out32)
+            out32[i] = __half2float(h);
+    }
+}
+__global__ void half_to_float_kernel(const __half* __restrict__ x, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __half2float(x[i]);
+}
+
 __global__ void fill_float_kernel(float* out, int64_t n, float v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
@@ -296,6 +312,8 @@ void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t*
         maxQ = std::min<idx_t>(maxQ, (idx_t)(kSearchPageBytes / (sizeof(float) * d)));
     maxQ = std::min<idx_t>(maxQ, (idx_t)((size_t(1) << 30) / ((size_t)k * 12 * 8)));
     maxQ = std::max<idx_t>(maxQ, 1);
+    if (hostQueries && (size_t)n * d * sizeof(float) >= minPagedSize_ && searchFromCpuPaged_(n, x, k, distances, labels, maxQ))
+        return;
     for (idx_t i0 = 0; i0 < n; i0 += maxQ) {
         InterruptCallback::check(); // between query pages
         const idx_t nb = std::min(maxQ, n - i0);
@@ -308,6 +326,109 @@ void GpuIndex::search(idx_t n, const float* x, idx_t k, float* distances, idx_t*
         if (dv.staged || lv.staged || xv.hold.data)
             CUDA_VERIFY(cudaStreamSynchronize(stream));
     }
+}
+
+// Host-resident queries above the paging threshold (role of searchFromCpuPaged_, faiss/gpu/GpuIndex.cu:620-788): the
+// pinned staging buffer of the resources object is split in two halves; a stager thread copies page p+1 into its
+// pinned half and queues the H2D copy on the async-copy stream while the calling thread searches page p on the
+// default stream.  (searchImpl_ synchronises with the host -- certificate flags, list offsets -- so the overlap needs
+// a second host thread rather than the reference's single-thread event chain.)  Returns false when there is no
+// pinned memory to page through; the caller then takes the plain loop.
+bool GpuIndex::searchFromCpuPaged_(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, idx_t maxQ) const {
+    auto pinned = resources_->getPinnedMemory();
+    const size_t half = pinned.second / 2;
+    const idx_t pageQ = std::min<idx_t>(maxQ, (idx_t)(half / (sizeof(float) * d)));
+    if (!pinned.first || pageQ < 1 || n <= pageQ)
+        return false;
+    auto stream = stream_();
+    auto copyStream = resources_->getAsyncCopyStream(config_.device);
+    const idx_t numPages = ceil_div(n, pageQ);
+    GpuMemoryReservation devBuf[2] = {
+            resources_->temp(config_.device, sizeof(float) * (size_t)pageQ * d),
+            resources_->temp(config_.device, sizeof(float) * (size_t)pageQ * d)};
+    float* pin[2] = {reinterpret_cast<float*>(pinned.first), reinterpret_cast<float*>((char*)pinned.first + half)};
+    cudaEvent_t ready[2];
+    for (auto& e : ready)
+        CUDA_VERIFY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+    std::mutex mu;
+    std::condition_variable cv;
+    idx_t issued = 0;   // pages whose H2D has been queued
+    idx_t consumed = 0; // pages whose search has finished (their buffers are free again)
+    bool abort = false;
+    std::string stagerError;
+    const int device = config_.device;
+    std::thread stager([&] {
+        try {
+            CUDA_VERIFY(cudaSetDevice(device));
+            for (idx_t p = 0; p < numPages; p++) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return abort || p < consumed + 2; });
+                    if (abort)
+                        return;
+                }
+                const int b = (int)(p & 1);
+                const idx_t i0 = p * pageQ, nb = std::min(pageQ, n - i0);
+                const size_t bytes = sizeof(float) * (size_t)nb * d;
+                std::memcpy(pin[b], x + (size_t)i0 * d, bytes);
+                CUDA_VERIFY(cudaMemcpyAsync(devBuf[b].data, pin[b], bytes, cudaMemcpyHostToDevice, copyStream));
+                CUDA_VERIFY(cudaEventRecord(ready[b], copyStream));
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    issued = p + 1;
+                }
+                cv.notify_all();
+            }
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            stagerError = e.what();
+            abort = true;
+            cv.notify_all();
+        }
+    });
+    auto finish = [&](bool failed) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (failed)
+                abort = true;
+        }
+        cv.notify_all();
+        stager.join();
+        cudaStreamSynchronize(copyStream);
+        for (auto& e : ready)
+            cudaEventDestroy(e);
+    };
+    try {
+        for (idx_t p = 0; p < numPages; p++) {
+            InterruptCallback::check(); // between query pages
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort || issued > p; });
+                if (abort)
+                    FB_THROW_FMT("query staging failed: %s", stagerError.c_str());
+            }
+            const int b = (int)(p & 1);
+            const idx_t i0 = p * pageQ, nb = std::min(pageQ, n - i0);
+            CUDA_VERIFY(cudaStreamWaitEvent(stream, ready[b], 0));
+            DeviceOut<float> dv(resources_.get(), config_.device, distances + (size_t)i0 * k, (size_t)nb * k);
+            DeviceOut<idx_t> lv(resources_.get(), config_.device, labels + (size_t)i0 * k, (size_t)nb * k);
+            searchImpl_(nb, devBuf[b].as<float>(), (int)k, dv.ptr, lv.ptr);
+            dv.finish(stream);
+            lv.finish(stream);
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                consumed = p + 1;
+            }
+            cv.notify_all();
+        }
+    } catch (...) {
+        finish(true);
+        throw;
+    }
+    finish(false);
+    return true;
 }
 
 void GpuIndex::compute_residual(const float* x, float* residual, idx_t key) const {
@@ -328,6 +449,7 @@ GpuIndexFlat::GpuIndexFlat(
         : GpuIndex(std::move(resources), dims, metric, 0, config),
           flatConfig_(config),
           vecs_(resources_.get(), config.device, AllocType::FlatData),
+          vecs16_(resources_.get(), config.device, AllocType::FlatData),
           y16_(resources_.get(), config.device, AllocType::FlatData),
           bias_(resources_.get(), config.device, AllocType::FlatData),
           perm_(resources_.get(), config.device, AllocType::FlatData),
@@ -341,6 +463,7 @@ GpuIndexFlat::~GpuIndexFlat() {}
 void GpuIndexFlat::reset() {
     DeviceScope scope(config_.device);
     vecs_.clear();
+    vecs16_.clear();
     y16_.clear();
     bias_.clear();
     perm_.clear();
@@ -375,14 +498,41 @@ void GpuIndexFlat::add_with_ids(idx_t n, const float* x, const idx_t* ids) {
 void GpuIndexFlat::addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) {
     FB_THROW_IF_NOT_MSG(idsDev == nullptr, "add_with_ids not supported");
     auto stream = stream_();
-    vecs_.append(xDev, (size_t)n * d, stream);
+    if (flatConfig_.useFloat16) {
+        const size_t old = vecs16_.size(), cnt = (size_t)n * d;
+        vecs16_.resize(old + cnt, stream);
+        float_to_half_kernel<<<(unsigned)std::min<size_t>(ceil_div(cnt, (size_t)256), 65535 * 16), 256, 0, stream>>>(
+                xDev, vecs16_.data() + old, nullptr, (int64_t)cnt);
+        CUDA_CHECK_LAST();
+    } else {
+        vecs_.append(xDev, (size_t)n * d, stream);
+    }
     this->ntotal += n;
     tcDirty_ = true;
+}
+
+const float* GpuIndexFlat::roundedQueries_(idx_t n, const float* xDev, GpuMemoryReservation& hold) const {
+    if (!flatConfig_.useFloat16 || n == 0)
+        return xDev;
+    auto stream = stream_();
+    const size_t cnt = (size_t)n * d;
+    hold = resources_->temp(config_.device, sizeof(float) * cnt);
+    float_to_half_kernel<<<(unsigned)std::min<size_t>(ceil_div(cnt, (size_t)256), 65535 * 16), 256, 0, stream>>>(
+            xDev, nullptr, hold.as<float>(), (int64_t)cnt);
+    CUDA_CHECK_LAST();
+    return hold.as<float>();
 }
 
 void GpuIndexFlat::replaceVectorsDevice(idx_t n, const float* xDev) {
     DeviceScope scope(config_.device);
     auto stream = stream_();
+    if (flatConfig_.useFloat16) {
+        vecs16_.resize(0, stream);
+        this->ntotal = 0;
+        if (n > 0)
+            addImpl_(n, xDev, nullptr);
+        return;
+    }
     vecs_.resize((size_t)n * d, stream); // keeps the allocation when it is large enough
     if (n > 0)
         CUDA_VERIFY(cudaMemcpyAsync(vecs_.data(), xDev, sizeof(float) * n * d, cudaMemcpyDeviceToDevice, stream));
@@ -407,7 +557,7 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
     auto scal = resources_->temp(config_.device, sizeof(float) * 2);
     auto norms = resources_->temp(config_.device, sizeof(float) * n);
     CUDA_VERIFY(cudaMemsetAsync(scal.data, 0, sizeof(float) * 2, stream));
-    runAbsMax(vecs_.data(), n * (int64_t)d, scal.as<float>(), stream);
+    runAbsMax(rows_(), n * (int64_t)d, scal.as<float>(), stream, yHalf_());
     float h[2] = {0.f, 0.f};
     CUDA_VERIFY(cudaMemcpyAsync(h, scal.data, sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
@@ -420,8 +570,8 @@ void GpuIndexFlat::prepareTensorCoreData_() const {
     fill_float_kernel<<<(unsigned)ceil_div(padRows, 256), 256, 0, stream>>>(bias_.data(), padRows, -INFINITY);
     CUDA_CHECK_LAST();
     runFlatTcPrepareRows(
-            resources_.get(), config_.device, vecs_.data(), n, d, dpad_, scale, metric_type, y16_.data(), bias_.data(),
-            sorted ? perm_.data() : nullptr, tileMaxBias_.data(), norms.as<float>(), stream);
+            resources_.get(), config_.device, rows_(), n, d, dpad_, scale, metric_type, y16_.data(), bias_.data(),
+            sorted ? perm_.data() : nullptr, tileMaxBias_.data(), norms.as<float>(), stream, yHalf_());
     runMaxOf(norms.as<float>(), n, scal.as<float>() + 1, stream);
     CUDA_VERIFY(cudaMemcpyAsync(h, scal.data, sizeof(float) * 2, cudaMemcpyDeviceToHost, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
@@ -445,18 +595,20 @@ void GpuIndexFlat::searchImpl_(idx_t n, const float* xDev, int k, float* dDev, i
     }
     // the tensor-core path pays a fixed cost per query tile of 128; tiny batches stay exact
     const bool tc = flatConfig_.useTensorCores && flatTcSupported(d, k, this->ntotal) && n >= 16;
+    GpuMemoryReservation qHold;
+    xDev = roundedQueries_(n, xDev, qHold);
     if (tc) {
         prepareTensorCoreData_();
         runFlatTcSearch(
-                resources_.get(), config_.device, xDev, n, vecs_.data(), y16_.data(), bias_.data(),
+                resources_.get(), config_.device, xDev, n, rows_(), y16_.data(), bias_.data(),
                 metric_type == METRIC_L2 ? perm_.data() : nullptr, tileMaxBias_.data(), yScale_,
-                yMaxNorm_, this->ntotal, d, dpad_, k, metric_type, dDev, iDev, stream);
+                yMaxNorm_, this->ntotal, d, dpad_, k, metric_type, dDev, iDev, stream, nullptr, yHalf_());
         lastSearchUsedTensorCores = 1;
         lastSearchFallbackQueries = lastFlatTcFallbacks();
     } else {
         runFlatExact(
-                resources_.get(), config_.device, xDev, n, vecs_.data(), this->ntotal, d, k, metric_type, 0, dDev, iDev,
-                stream);
+                resources_.get(), config_.device, xDev, n, rows_(), this->ntotal, d, k, metric_type, 0, dDev, iDev,
+                stream, yHalf_());
     }
 }
 
@@ -472,10 +624,12 @@ void GpuIndexFlat::searchShardDevice(idx_t n, const float* xDev, int k, float* d
     FB_THROW_IF_NOT_MSG(shardPoolingEligible(k, n), "pooled sharded search requested on a shard that cannot take the tensor-core path");
     auto stream = stream_();
     prepareTensorCoreData_();
+    GpuMemoryReservation qHold;
+    xDev = roundedQueries_(n, xDev, qHold);
     runFlatTcSearch(
-            resources_.get(), config_.device, xDev, n, vecs_.data(), y16_.data(), bias_.data(),
+            resources_.get(), config_.device, xDev, n, rows_(), y16_.data(), bias_.data(),
             metric_type == METRIC_L2 ? perm_.data() : nullptr, tileMaxBias_.data(), yScale_, yMaxNorm_, this->ntotal, d,
-            dpad_, k, metric_type, dDev, iDev, stream, flatShard);
+            dpad_, k, metric_type, dDev, iDev, stream, flatShard, yHalf_());
     lastSearchUsedTensorCores = 1;
     lastSearchFallbackQueries = lastFlatTcFallbacks();
 }
@@ -490,6 +644,20 @@ void GpuIndexFlat::reconstruct_n(idx_t i0, idx_t num, float* out) const {
         return;
     FB_THROW_IF_NOT_MSG(i0 >= 0 && i0 + num <= this->ntotal, "reconstruct: index out of bounds");
     auto stream = stream_();
+    if (flatConfig_.useFloat16) { // widen through a device buffer, 64 MiB of fp32 at a time
+        const idx_t step = std::max<idx_t>(1, (idx_t)((size_t(64) << 20) / (sizeof(float) * d)));
+        for (idx_t r = 0; r < num; r += step) {
+            const idx_t m = std::min(step, num - r);
+            const size_t cnt = (size_t)m * d;
+            DeviceOut<float> ov(resources_.get(), config_.device, out + (size_t)r * d, cnt);
+            half_to_float_kernel<<<(unsigned)std::min<size_t>(ceil_div(cnt, (size_t)256), 65535 * 16), 256, 0, stream>>>(
+                    vecs16_.data() + (size_t)(i0 + r) * d, ov.ptr, (int64_t)cnt);
+            CUDA_CHECK_LAST();
+            ov.finish(stream);
+            CUDA_VERIFY(cudaStreamSynchronize(stream));
+        }
+        return;
+    }
     CUDA_VERIFY(cudaMemcpyAsync(out, vecs_.data() + (size_t)i0 * d, sizeof(float) * num * d, cudaMemcpyDefault, stream));
     CUDA_VERIFY(cudaStreamSynchronize(stream));
 }
@@ -501,7 +669,7 @@ void GpuIndexFlat::reconstruct_batch(idx_t n, const idx_t* keys, float* out) con
     auto stream = stream_();
     DeviceView<idx_t> kv(resources_.get(), config_.device, keys, n, stream);
     DeviceOut<float> ov(resources_.get(), config_.device, out, (size_t)n * d);
-    runGatherRows(vecs_.data(), kv.ptr, n, d, ov.ptr, stream);
+    runGatherRows(rows_(), kv.ptr, n, d, ov.ptr, stream, yHalf_());
     ov.finish(stream);
     CUDA_VERIFY(cudaStreamSynchronize(stream));
 }
@@ -518,7 +686,7 @@ void GpuIndexFlat::compute_residual_n(idx_t n, const float* xs, float* residuals
     DeviceView<float> xv(resources_.get(), config_.device, xs, (size_t)n * d, stream);
     DeviceView<idx_t> kv(resources_.get(), config_.device, keys, n, stream);
     DeviceOut<float> ov(resources_.get(), config_.device, residuals, (size_t)n * d);
-    runCalcResidual(xv.ptr, vecs_.data(), kv.ptr, n, d, ov.ptr, stream);
+    runCalcResidual(xv.ptr, rows_(), kv.ptr, n, d, ov.ptr, stream, yHalf_());
     ov.finish(stream);
     CUDA_VERIFY(cudaStreamSynchronize(stream));
 }

@@ -184,6 +184,8 @@ class GpuIndex : public Index {
     virtual bool addImplRequiresIDs_() const = 0;
     virtual void addImpl_(idx_t n, const float* xDev, const idx_t* idsDev) = 0;
     virtual void searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const = 0;
+    // host queries above the paging threshold: pinned double buffers + async-copy stream (GpuIndex.cu:620-788)
+    bool searchFromCpuPaged_(idx_t n, const float* x, idx_t k, float* distances, idx_t* labels, idx_t maxQ) const;
 
    public:
     // Shard-local half of a sharded search (device pointers, ids local to this shard).  `flatShard` is
@@ -214,7 +216,7 @@ class GpuIndex : public Index {
 // GpuIndexFlat
 // ------------------------------------------------------------------------------------------
 struct GpuIndexFlatConfig : GpuIndexConfig { // faiss/gpu/GpuIndexFlat.h:26-35
-    bool useFloat16 = false;        // accepted for API compatibility; storage stays fp32
+    bool useFloat16 = false;        // store the vectors as fp16; queries are rounded to fp16 too (FlatIndex.cu:112-136)
     bool useTensorCores = true;     // false: always take the exact SIMT kernel
 };
 
@@ -251,8 +253,12 @@ class GpuIndexFlat : public GpuIndex {
     }
     void searchShardDevice(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev, const FlatTcShard* flatShard) const override;
     bool shardPoolingEligible(int k, idx_t n) const override;
-    const float* vectorsDevice() const {
+    const float* vectorsDevice() const { // fp32 rows (IVF coarse centroids); not available under useFloat16
+        FB_THROW_IF_NOT_MSG(!flatConfig_.useFloat16, "fp32 row access on a float16 GpuIndexFlat");
         return vecs_.data();
+    }
+    bool usesFloat16() const {
+        return flatConfig_.useFloat16;
     }
     void setUseTensorCores(bool v) {
         flatConfig_.useTensorCores = v;
@@ -272,8 +278,19 @@ class GpuIndexFlat : public GpuIndex {
     void searchImpl_(idx_t n, const float* xDev, int k, float* dDev, idx_t* iDev) const override;
     void prepareTensorCoreData_() const;
 
+    const void* rows_() const { // the stored rows, as the kernels take them (with yHalf_())
+        return flatConfig_.useFloat16 ? (const void*)vecs16_.data() : (const void*)vecs_.data();
+    }
+    int yHalf_() const {
+        return flatConfig_.useFloat16 ? 1 : 0;
+    }
+    // useFloat16: the query block rounded to fp16 and widened again (what the reference's convertTensor does before
+    // its half GEMM); returns x itself otherwise
+    const float* roundedQueries_(idx_t n, const float* xDev, GpuMemoryReservation& hold) const;
+
     GpuIndexFlatConfig flatConfig_;
-    DeviceVector<float> vecs_;
+    DeviceVector<float> vecs_;    // fp32 storage (default)
+    DeviceVector<__half> vecs16_; // fp16 storage (useFloat16): the only copy of the vectors besides the scoring tiles
     // tensor-core side data, rebuilt lazily after adds
     mutable DeviceVector<__half> y16_;
     mutable DeviceVector<float> bias_;

@@ -18,12 +18,13 @@ void runL2Norms(const float* x, int64_t n, int d, float* norms, cudaStream_t str
 // tensor-core path, and the canonical arithmetic the tensor-core re-rank reproduces.
 // Role of runDistance<float> (faiss/gpu/impl/Distance.cu:121-405) with the k-select fused in.
 //   Q [nq,d], Y [n,d] row-major; outD [nq,k], outI [nq,k] (int64, row index + idBase; -1 missing)
+//   yHalf: Y holds __half rows (GpuIndexFlatConfig::useFloat16 storage), widened to fp32 on load
 void runFlatExact(
         GpuResources* res,
         int device,
         const float* Q,
         int64_t nq,
-        const float* Y,
+        const void* Y,
         int64_t n,
         int d,
         int k,
@@ -31,7 +32,8 @@ void runFlatExact(
         int64_t idBase,
         float* outD,
         idx_t* outI,
-        cudaStream_t stream);
+        cudaStream_t stream,
+        int yHalf = 0);
 
 // k = 1 convenience (assignment): outI int64 [nq], outD optional
 void runFlatArgmin(
@@ -83,14 +85,15 @@ void runMergeTopKListMajor(
 // residual x - c[assign] (NaN if assign = -1) ; role of runCalcResidual (VectorResidual.cu:26-176)
 void runCalcResidual(
         const float* x,
-        const float* centroids,
+        const void* centroids,
         const idx_t* assign,
         int64_t n,
         int d,
         float* out,
-        cudaStream_t stream);
+        cudaStream_t stream,
+        int yHalf = 0);
 // gather rows by id (reconstruct_batch) / by range
-void runGatherRows(const float* src, const idx_t* ids, int64_t n, int d, float* out, cudaStream_t stream);
+void runGatherRows(const void* src, const idx_t* ids, int64_t n, int d, float* out, cudaStream_t stream, int yHalf = 0);
 
 // ---------------------------------------------------------------- flat_tc.cu  (tcgen05 path)
 struct FlatTcPlan; // opaque: tensor maps + scratch sizing for one (index, nq, k) shape
@@ -101,7 +104,7 @@ struct FlatTcPlan; // opaque: tensor maps + scratch sizing for one (index, nq, k
 void runFlatTcPrepareRows(
         GpuResources* res,
         int device,
-        const float* Y,
+        const void* Y, // fp32 rows, or __half rows when yHalf
         int64_t n,
         int d,
         int dpad,
@@ -112,10 +115,11 @@ void runFlatTcPrepareRows(
         int* perm,
         float* tileMaxBias,
         float* norms,
-        cudaStream_t stream);
+        cudaStream_t stream,
+        int yHalf = 0);
 
 // max |x| over a matrix (device scalar, float) -- used to pick the power-of-two fp16 scale
-void runAbsMax(const float* x, int64_t count, float* out /*device, must be zeroed*/, cudaStream_t stream);
+void runAbsMax(const void* x, int64_t count, float* out /*device, must be zeroed*/, cudaStream_t stream, int yHalf = 0);
 // max row norm^2
 void runMaxOf(const float* x, int64_t count, float* out /*device, zeroed; x >= 0*/, cudaStream_t stream);
 
@@ -137,7 +141,7 @@ void runFlatTcSearch(
         int device,
         const float* Q,
         int64_t nq,
-        const float* Y,      // fp32 rows [n,d] (exact re-rank)
+        const void* Y,       // stored rows [n,d] (exact re-rank): fp32, or __half when yHalf
         const __half* Y16,   // fp16 scaled rows [n,dpad], stored order
         const float* bias,   // [n] stored order
         const int* perm,     // stored position -> row id (null: identity)
@@ -152,7 +156,8 @@ void runFlatTcSearch(
         float* outD,
         idx_t* outI,
         cudaStream_t stream,
-        const FlatTcShard* shard = nullptr);
+        const FlatTcShard* shard = nullptr,
+        int yHalf = 0);
 
 // number of queries the last runFlatTcSearch on this thread recomputed with the exact kernel
 int& lastFlatTcFallbacks();

@@ -90,9 +90,19 @@ FB200_API int faiss_Index_reconstruct_batch(const FaissIndex* index, idx_t n, co
 FB200_API int faiss_Index_compute_residual(const FaissIndex* index, const float* x, float* residual, idx_t key);
 FB200_API int faiss_Index_compute_residual_n(const FaissIndex* index, idx_t n, const float* x, float* residuals, const idx_t* keys);
 
+/* GpuIndex::setMinPagingSize / getMinPagingSize (faiss/gpu/GpuIndex.h:66-69): host-resident query blocks of at least
+ * this many bytes (default 256 MiB) are paged through the resources' pinned buffer, H2D of page p+1 overlapping the
+ * search of page p (role of searchFromCpuPaged_, faiss/gpu/GpuIndex.cu:620-788). */
+FB200_API int faiss_GpuIndex_setMinPagingSize(FaissGpuIndex* index, size_t size);
+FB200_API int faiss_GpuIndex_getMinPagingSize(const FaissGpuIndex* index, size_t* out_size);
+
 /* ---- GpuIndexFlat (faiss/gpu/GpuIndexFlat.h:43-217) ---- */
 /* use_tensor_cores: 1 = tcgen05 path when the shape supports it (default), 0 = exact SIMT only */
 FB200_API int faiss_GpuIndexFlat_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, FaissMetricType metric, int device, int use_tensor_cores);
+/* GpuIndexFlatConfig (faiss/gpu/GpuIndexFlat.h:26-35).  use_float16: the vectors are stored as fp16 and queries are
+ * rounded to fp16 before the comparison, as FlatIndex::query does (faiss/gpu/impl/FlatIndex.cu:112-136); distances are
+ * the exact fp32 distances between the rounded values. */
+FB200_API int faiss_GpuIndexFlat_new_with_config(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, FaissMetricType metric, int device, int use_tensor_cores, int use_float16);
 FB200_API int faiss_GpuIndexFlatL2_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, int device);
 FB200_API int faiss_GpuIndexFlatIP_new(FaissGpuIndex** p_index, FaissStandardGpuResources* res, int d, int device);
 /* copyFrom / copyTo against the CPU IndexFlat payload (faiss/gpu/GpuIndexFlat.cu:105-176) */

@@ -71,7 +71,9 @@ def test_golden_integer_regime_bit_exact(res, golden, k):
 
 
 @pytest.mark.parametrize("metric", [1, 0])
-@pytest.mark.parametrize("N,d,nq,k", [(70000, 128, 300, 100), (120000, 96, 130, 10), (50000, 64, 64, 1), (65000, 100, 40, 50), (40000, 128, 520, 512)])
+@pytest.mark.parametrize("N,d,nq,k", [(70000, 128, 300, 100), (120000, 96, 130, 10), (50000, 64, 64, 1), (65000, 100, 40, 50), (40000, 128, 520, 512),
+     # K-split kernel (128 < d <= 256: ring stages hold single K-blocks) and the large-k lists
+     (70000, 192, 300, 100), (66000, 256, 530, 10), (50000, 130, 100, 33), (90000, 64, 300, 1024), (100000, 32, 70, 2048), (40000, 256, 64, 2048)])
 def test_tensor_core_path_equals_exact_path(res, N, d, nq, k, metric):
     """tcgen05 scoring + certified re-rank must be indistinguishable from the exact kernel"""
     import torch
@@ -144,7 +146,7 @@ def test_tcgen05_raw_scores(res):
     import faiss_b200 as fb
 
     torch.manual_seed(0)
-    for nq, N, dpad in [(128, 256, 64), (200, 1000, 128), (300, 5000, 128)]:
+    for nq, N, dpad in [(128, 256, 64), (200, 1000, 128), (300, 5000, 128), (300, 5000, 192), (520, 9000, 256)]:
         Q = torch.randn(nq, dpad, device="cuda").half()
         Y = torch.randn(N, dpad, device="cuda").half()
         S = fb.flat_tc_scores_debug(res, Q, Y)
@@ -233,7 +235,7 @@ def test_memory_info_and_oom(res):
 
 
 @pytest.mark.parametrize("metric", [1, 0])
-@pytest.mark.parametrize("N,d,nq", [(4096, 128, 3000), (70000, 96, 5000), (2048, 64, 17), (300000, 32, 700)])
+@pytest.mark.parametrize("N,d,nq", [(4096, 128, 3000), (70000, 96, 5000), (2048, 64, 17), (300000, 32, 700), (30000, 256, 2000), (5000, 160, 300)])
 def test_streaming_argmin_equals_exact_path(res, N, d, nq, metric):
     """k = 1 takes the streaming tcgen05 mode (self-tightening thresholds, fused select + re-rank): the k-means
     assignment path.  Must be indistinguishable from the exact kernel, ids and distances."""
@@ -294,3 +296,63 @@ def test_bfknn_free_function(res, metric):
     assert np.array_equal(I, Id.cpu().numpy()) and np.array_equal(D, Dd.cpu().numpy())
     with pytest.raises(fb.FaissError):
         fb.bfKnn(res, xq, xb, 5000, metric)
+
+
+@pytest.mark.parametrize("metric", [1, 0])
+@pytest.mark.parametrize("N,d,nq,k,tc", [(3000, 32, 24, 10, False), (70000, 128, 300, 100, True), (50000, 64, 200, 1, True), (40000, 50, 33, 7, True)])
+def test_float16_storage(res, N, d, nq, k, tc, metric):
+    """GpuIndexFlatConfig::useFloat16 (faiss/gpu/GpuIndexFlat.h:26-35; the reference's TestGpuIndexFlat Float16 cases):
+    vectors and queries are rounded to fp16, distances are exact between the rounded values -- i.e. a CPU IndexFlat over
+    the rounded data.  Both paths (tcgen05 + certified re-rank, exact SIMT) must agree bit for bit."""
+    import faiss_b200 as fb
+
+    xb = o.float_rand(N * d, 91).reshape(N, d)
+    xq = o.float_rand(nq * d, 92).reshape(nq, d)
+    idx = fb.GpuIndexFlat(res, d, metric, use_float16=True)
+    idx.add(xb[: N // 2])
+    idx.add(xb[N // 2 :])
+    D, I = idx.search(xq, k)
+    assert idx.lastSearchInfo()["tensor_cores"] == int(tc)
+    xb16 = xb.astype(np.float16).astype(np.float32)
+    xq16 = xq.astype(np.float16).astype(np.float32)
+    rD, rI = _ref_search(xb16, xq16, k, metric)
+    o.compare_lists(rD, rI, D, I, eps=1e-4, pct_max_diff1=0.01, pct_max_diffN=0.002)
+    idx.setUseTensorCores(False)
+    De, Ie = idx.search(xq, k)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+    # the stored payload is the rounded data
+    assert np.array_equal(idx.reconstruct_n(5, 40), xb16[5:45])
+    assert np.array_equal(idx.copyTo(), xb16)
+    keys = np.array([3, N - 1, 17], dtype=np.int64)
+    assert np.array_equal(idx.reconstruct_batch(keys), xb16[keys])
+    r = idx.compute_residual_n(xq[:3], keys)
+    assert np.array_equal(r, xq[:3] - xb16[keys])
+
+
+def test_host_query_paging_pipeline():
+    """searchFromCpuPaged_ (faiss/gpu/GpuIndex.cu:620-788): host queries above getMinPagingSize go through the pinned
+    double buffer (stager thread + async-copy stream); the result must be the unpaged one, page boundaries included."""
+    import faiss_b200 as fb
+
+    res = fb.StandardGpuResources()
+    res.setPinnedMemory(1 << 20)  # two 512 KiB halves -> 2048 queries of d = 64 per page
+    rs = np.random.RandomState(5)
+    xb = rs.rand(40000, 64).astype(np.float32)
+    xq = rs.rand(2048 * 3 + 77, 64).astype(np.float32)  # 4 pages, ragged tail
+    for make in (lambda: fb.GpuIndexFlatL2(res, 64), lambda: fb.GpuIndexIVFFlat(res, 64, 32, fb.METRIC_L2)):
+        idx = make()
+        if not idx.is_trained:
+            idx.train(xb[:8000])
+            idx.nprobe = 4
+        idx.add(xb)
+        assert idx.getMinPagingSize() == 256 << 20
+        D0, I0 = idx.search(xq, 10)  # below the threshold: one block
+        idx.setMinPagingSize(1 << 16)
+        assert idx.getMinPagingSize() == 1 << 16
+        D1, I1 = idx.search(xq, 10)
+        assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+        # k = 1 (streaming path) and a single-query tail page
+        D2, I2 = idx.search(xq[: 2048 * 2 + 1], 1)
+        idx.setMinPagingSize(256 << 20)
+        D3, I3 = idx.search(xq[: 2048 * 2 + 1], 1)
+        assert np.array_equal(I2, I3) and np.array_equal(D2, D3)
