@@ -542,7 +542,8 @@ __global__ void tc_rerank_kernel(
     const float tq = thr ? thr[q] : -CUDART_INF_F;
     for (int e0 = 0; e0 < LIST; e0 += 32) {
         int id = bi[e0 + lane];
-        bool valid = id != IdLimits<int>::max();
+        const bool present = id != IdLimits<int>::max();
+        bool valid = present;
         if (valid && thr)
             valid = -baseKey[(int64_t)q * LIST + e0 + lane] > tq;
         if (valid && perm)
@@ -583,8 +584,10 @@ __global__ void tc_rerank_kernel(
             if (!IS_L2)
                 acc = -acc;
         }
-        // the base list is sorted by approximate score, sentinels at the end
-        if (!__any_sync(kFullMask, valid))
+        // valid entries are packed at the front of the base list, sentinels behind them.  The list is NOT ordered by
+        // score (bisection select), so entries the pooled threshold excludes can sit anywhere: only a group made of
+        // sentinels ends the walk.
+        if (!__any_sync(kFullMask, present))
             break;
         w.add(valid, acc, id);
     }
@@ -956,6 +959,7 @@ void runFlatTcScoresDebug(
     p.numTiles = (unsigned long long)numTiles;
     p.KB = KB;
     p.ksplit = sp.ksplit;
+    p.kSteps = dpad / 16; // debug seam: operands arrive padded
     p.yStages = sp.yStages;
     p.invScalePtr = one;
     p.bias = nullptr;
@@ -1166,6 +1170,7 @@ void runFlatTcSearch(
             p.numTiles = (unsigned long long)T;
             p.KB = KB;
             p.ksplit = sp.ksplit;
+            p.kSteps = (d + 15) / 16;
             p.yStages = sp.yStages;
             p.invScalePtr = sc + 2;
             p.bias = bias;

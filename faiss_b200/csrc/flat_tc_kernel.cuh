@@ -55,6 +55,7 @@ struct TcParams {
     int tilesPerSlice;
     unsigned long long permA, permB, numTiles;
     int KB;             // dpad / 64
+    int kSteps;         // ceil(d / 16): 16-wide MMA K-steps that hold data; the zero padding up to dpad is never issued
     int ksplit;         // 1: a ring stage holds ONE 64-wide K-block of a database tile (128 < d <= 256), else a whole tile
     int yStages;
     const float* invScalePtr; // device scalar: 1 / (qScale * yScale)
@@ -279,8 +280,8 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                                 ptx::mbar_wait(&y_full[ys], yphase);
                                 ptx::tc_fence_after();
                                 const uint32_t yaddr = sYaddr + (uint32_t)ys * (uint32_t)stageBytes;
-#pragma unroll
-                                for (int k4 = 0; k4 < 4; k4++) {
+                                const int k4n = min(4, p.kSteps - 4 * kb);
+                                for (int k4 = 0; k4 < k4n; k4++) {
                                     uint64_t da = ptx::make_smem_desc_sw128(qaddr + kb * qkb + k4 * 32);
                                     uint64_t db = ptx::make_smem_desc_sw128(yaddr + k4 * 32);
                                     ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
@@ -305,13 +306,12 @@ __global__ void __launch_bounds__(tcThreads(PARTS), 1) flat_tc_kernel(
                         ptx::tc_fence_after();
                         const uint32_t dcol = tmem_base + (uint32_t)h * kTileN;
                         const uint32_t qaddr = sQaddr + (uint32_t)h * (uint32_t)qBytes;
-                        for (int kb = 0; kb < p.KB; kb++) {
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; k4++) {
-                                uint64_t da = ptx::make_smem_desc_sw128(qaddr + kb * qkb + k4 * 32);
-                                uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * ykb + k4 * 32);
-                                ptx::mma_f16_ss(dcol, da, db, idesc, (kb | k4) != 0 ? 1u : 0u);
-                            }
+                        // (d = 96: 6 of the 8 K-steps of the padded tile -- a quarter of the tensor work is zeros otherwise)
+                        for (int ks = 0; ks < p.kSteps; ks++) {
+                            const int kb = ks >> 2, k4 = ks & 3;
+                            uint64_t da = ptx::make_smem_desc_sw128(qaddr + kb * qkb + k4 * 32);
+                            uint64_t db = ptx::make_smem_desc_sw128(yaddr + kb * ykb + k4 * 32);
+                            ptx::mma_f16_ss(dcol, da, db, idesc, ks != 0 ? 1u : 0u);
                         }
                         ptx::mma_commit(&t_full[h]); // accumulator ready for the epilogue
                     }
