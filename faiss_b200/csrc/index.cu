@@ -1654,7 +1654,7 @@ void GpuIndexIVFPQ::trainResidualQuantizer_(idx_t n, const float* xDev) {
     auto stream = stream_();
     GpuResources* res = resources_.get();
     const int device = config_.device;
-    const int ksub = 256, dsub = d / M_;
+    const int ksub = 256;
     // fvecs_maybe_subsample (faiss/utils/utils.cpp:464-489) with pq.cp.seed
     const idx_t nmax = (idx_t)pq_cp.max_points_per_centroid * ksub;
     GpuMemoryReservation sub;

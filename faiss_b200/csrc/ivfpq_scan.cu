@@ -26,7 +26,6 @@ int ivfScanChunks(int device, int64_t nq, int nprobe, int* probesPerCta);
 
 namespace {
 
-constexpr int kBuf = 64;
 constexpr int kLutSlots = 64; // 256 B per code value
 
 __device__ __forceinline__ int64_t interleaved_pos(int64_t v, int j, int M) {
@@ -94,12 +93,6 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
     return v;
-}
-// packed add of two fp32 pairs (Blackwell FADD2): {a0,a1} += {v0,v1}, each lane-wise add is a plain RN fp32 add
-__device__ __forceinline__ void add2(float& a0, float& a1, float v0, float v1) {
-    asm("{\n.reg .b64 ra, rv, rd;\nmov.b64 ra, {%0,%1};\nmov.b64 rv, {%2,%3};\nadd.rn.f32x2 rd, ra, rv;\nmov.b64 {%0,%1}, rd;\n}"
-        : "+f"(a0), "+f"(a1)
-        : "f"(v0), "f"(v1));
 }
 
 // One CTA = one query x one chunk of its probes, kWarps warps.
