@@ -71,3 +71,32 @@ def test_distributed_index_shards_processes(world):
     for name in ("flat_float", "flat_int", "flat_ip_small", "ivfflat_idmod", "kmeans_sharded"):
         assert out[name]["ids_equal"] and out[name]["distances_equal"], (name, out[name])
     assert out["flat_float"]["tensor_cores"] == 1 and out["flat_float"]["device_queries_equal"]
+
+
+def test_index_shards_eight_way_pooled_thresholds():
+    """8 shards: the pooled threshold excludes most of a shard's (unsorted) base list -- a shard keeps ~k/8 of ~k
+    entries -- so the exact re-rank must walk the whole list.  The build that ended the walk at the first group of 32
+    entries without a survivor lost ~1.6 % of the ids here and nothing at 2 shards (CPU model:
+    tests/test_pooling_model.py)."""
+    if _ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    import faiss_b200 as fb
+
+    ndev = 8
+    res = fb.StandardGpuResources()
+    res.ncclInitAll(list(range(ndev)))
+    rs = np.random.RandomState(11)
+    N, d, nq, k = ndev * 60_000, 64, 2000, 100
+    xb = rs.rand(N, d).astype(np.float32)
+    xq = rs.rand(nq, d).astype(np.float32)
+    shards = fb.IndexShards(d, threaded=True, successive_ids=True)
+    subs = [fb.GpuIndexFlatL2(res, d, device=i) for i in range(ndev)]
+    for s in subs:
+        shards.add_shard(s)
+    shards.add(xb)
+    D, I = shards.search(xq, k)
+    assert shards.lastSearchPath() == "nccl"
+    full = fb.GpuIndexFlatL2(res, d, device=0, use_tensor_cores=False)
+    full.add(xb)
+    uD, uI = full.search(xq, k)
+    assert np.array_equal(I, uI) and np.array_equal(D, uD)
