@@ -55,7 +55,7 @@ def test_index_shards_nccl_fast_path_equals_unsharded():
     assert np.array_equal(I2, uI) and np.array_equal(D2, uD)
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_distributed_index_shards_processes(world):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
