@@ -689,6 +689,19 @@ def bfKnn(res, xq, xb, k, metric=METRIC_L2, device=0):
     return D, I
 
 
+def knn_gpu(res, xq, xb, k, D=None, I=None, metric=METRIC_L2, device=0):
+    """faiss.knn_gpu (faiss/python/gpu_wrappers.py:60-200) for row-major fp32 inputs: argument order of the reference,
+    optional preallocated outputs."""
+    rD, rI = bfKnn(res, xq, xb, k, metric, device)
+    if D is not None:
+        D[...] = rD
+        rD = D
+    if I is not None:
+        I[...] = rI
+        rI = I
+    return rD, rI
+
+
 def kmeans_sharded(res, x_local, k, niter=25, seed=1234, device=0):
     """Collective: k-means over the rows of ALL ranks of the device's NCCL communicator (this rank passes its own
     rows; rank order = row order).  Returns (centroids [k, d] identical on every rank, objective per iteration,
